@@ -1,0 +1,123 @@
+// ORACLE (test infrastructure, not product code).
+// Dependency-free CPU restatement of the LT-removert / LT-map per-keyframe hot path of
+// gisbi-kim/lt-mapper (reference @ 80b6756).  The reference itself cannot be built here (needs
+// ROS, PCL, FLANN, Eigen, OpenCV, Boost: SURVEY.md §8c), so this restatement is the parity
+// definition.  PARITY UNPINNED: the reference has no tests/golden vectors; third-party semantics
+// (PCL transformPointCloud, OctreePointCloudVoxelCentroid, KdTreeFLANN) are restated from their
+// published sources and flagged where used.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// include, link or execute this code.  The product (lt_mapper_b200/) never does.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <map>
+#include "ref_math.h"
+#include "kdtree.h"
+
+namespace ltr_oracle {
+
+struct Pt { float x, y, z, i; };          // pcl::PointXYZI payload (utility.h:90)
+typedef std::vector<Pt> Cloud;
+struct Mat4 { double m[16]; };             // row-major 4x4 (Session.cpp:109)
+
+static const float kFlagNoPOINT = 10000.0f;        // utility.h:93
+static const float kValidDiffUpperBound = 200.0f;  // utility.h:94
+
+enum PassMode { MODE_HD = 0, MODE_ND = 1, MODE_PD = 2 };
+
+struct Params {
+    float vfov = 50.0f, hfov = 360.0f;              // RosParamServer.cpp:15-17
+    Mat4 lidar2base, base2lidar;                    // kSE3MatExtrinsicLiDARtoPoseBase / its inverse (RosParamServer.cpp:28-30)
+    int transform_order = 0;                        // see ref_math.h transformPoint
+    int num_knn = 2;                                // removert/num_nn_points_within (yaml :65)
+    float knn_thr = 0.01f;                          // removert/dist_nn_points_within (yaml :66), applied to mean SQUARED distance
+    float downsample_voxel = 0.05f;                 // removert/downsample_voxel_size
+    int threads = 1;                                // deterministic OMP over keyframes
+    int faithful = 0;                               // 1 = reference-like structure for TIMING only: materialised two-step
+                                                    //     transforms (serial), racy OMP per-pixel min (utility.cpp:110)
+    int omp_cores = 16;                             // num_omp_cores (yaml :69) used in faithful mode
+    Params();
+};
+
+// ---- L0 free functions (utility.cpp) ----
+void scan2RangeImg(const Cloud& scan, const Params& p, int rows, int cols, std::vector<float>& rimg);               // Removerter.cpp:109-156
+void map2RangeImg(const Cloud& scan, const Params& p, int rows, int cols, std::vector<float>& rimg, std::vector<int>& ptidx);  // utility.cpp:92-142
+void transformPointCloud(const Cloud& in, Cloud& out, const Mat4& T, int order);                                   // pcl::transformPointCloud
+void transformGlobalMapToLocal(const Cloud& map_global, const Mat4& inv_pose, const Mat4& base2lidar, int order, Cloud& map_local);  // utility.cpp:64-72
+Cloud parseProjectedPoints(const Cloud& map_local, const Params& p, int rows, int cols);                          // utility.cpp:74-89
+Cloud local2global(const Cloud& scan_local, const Mat4& pose, const Mat4& lidar2base, int order);                 // utility.cpp:160-168
+Cloud global2local(const Cloud& scan_global, const Mat4& inv_pose, const Mat4& base2lidar, int order);            // utility.cpp:194-202
+Cloud mergeScansWithinGlobalCoordUtil(const std::vector<Cloud>& scans, const std::vector<Mat4>& poses, const Mat4& lidar2base, int order);  // utility.cpp:170-192
+int octreeDownsampling(const Cloud& src, Cloud& dst, float leaf);                                                 // utility.cpp:204-219 (0 ok, <0 unsupported input)
+Mat4 inverse4x4(const Mat4& a);                                                                                   // stands in for Eigen::Matrix4d::inverse() (Session.cpp:110)
+
+// ---- remove/revert/ND/PD pass (Removerter.cpp:381-593) ----
+// Returns the sorted unique dynamic map indices (std::set semantics, Removerter.cpp:589-590).
+std::vector<int> calcDescrepancyAndParseDynamicPointIdxForEachScan(
+    const Cloud& map_global, const std::vector<Cloud>& scans, const std::vector<Mat4>& inv_poses,
+    const Params& p, int mode, int rows, int cols, float diff_thres);
+// getStaticIdxFromDynamicIdx + parsePointcloudSubsetUsingPtIdx (Removerter.cpp:675-687, 933-946)
+int partitionByIdx(const Cloud& map, const std::vector<int>& dyn_idx, Cloud& stat, Cloud& dyn);
+
+// ---- kNN partition (Session.cpp:537-642) ----
+void partitionScanByKnn(const Cloud& scan_local, const Mat4& pose, const Mat4& inv_pose, const KdTree& target,
+                        const Params& p, int k, float thr, Cloud& coexist_local, Cloud& diff_local,
+                        std::vector<uint8_t>* labels /* optional: 1 = diff */);
+
+// ---- per-session state (Session.h:39-87) ----
+struct Session {
+    std::string sess_type_;
+    std::vector<Mat4> keyframe_poses_, keyframe_inverse_poses_;
+    std::vector<Cloud> keyframe_scans_;
+    std::vector<Cloud> keyframe_scans_static_projected_, keyframe_scans_dynamic_;
+    std::vector<Cloud> scans_knn_coexist_, scans_knn_diff_;
+    std::vector<Cloud> keyframe_scans_updated_, keyframe_scans_updated_strong_, keyframe_scans_pd_,
+        keyframe_scans_strong_pd_, keyframe_scans_strong_nd_, keyframe_scans_weak_nd_;
+    Cloud map_global_orig_, map_global_curr_, map_global_curr_static_, map_global_curr_dynamic_;
+    Cloud map_global_updated_, map_global_updated_strong_;
+    Cloud map_global_nd_, map_global_nd_strong_, map_global_nd_weak_;
+    Cloud map_global_pd_, map_global_pd_orig_, map_global_pd_strong_, map_global_pd_weak_;
+};
+
+struct ScheduleOp { int op; float res; };  // op 0 = removeOnce(res), 1 = resetAsDynamic; revertOnce(res); resetAsStatic
+enum { OP_REMOVE = 0, OP_REVERT = 1 };
+
+struct PassLog { std::string what; long n_map, n_dynamic, n_static_after, n_dynamic_after; };
+
+// ---- pipeline driver (Removerter.cpp) ----
+struct Removerter {
+    Params P;
+    Session central_sess_, query_sess_;
+    std::vector<ScheduleOp> hd_schedule;    // default: single removeOnce(2.5) as shipped (Removerter.cpp:1584,1587)
+    bool do_high_dyn_knn = true;            // extractHighDynPointsViaKnnDiff (viz output, Removerter.cpp:1591-1592)
+    std::vector<PassLog> log;
+    std::map<std::string, Cloud> saved;     // what the reference writes as PCD (Removerter.cpp:1446-1477, 1517-1520, 1600-1601)
+    std::map<std::string, double> timing;   // seconds per stage
+
+    Removerter();
+    void precleaningKeyframes(float radius);     // Session.cpp:506-533
+    void makeGlobalMap();                        // Removerter.cpp:213-252
+    void removeOnce(Session& t, const Session& s, float res);         // :882-905
+    void revertOnce(Session& t, const Session& s, float res);         // :908-931
+    void iremoveOnceForND(Session& t, const Session& s, float res);   // :831-854
+    void removeOnceForPD(Session& t, const Session& s, float res);    // :856-880
+    void runSchedule(Session& s);                // generalised selfRemovert (:1378-1393)
+    void removeHighDynamicPoints();              // :1580-1604
+    void parseScansViaProjection(const Session& s, const Cloud& map, std::vector<Cloud>& out);  // Session.cpp:348-360
+    void parseStaticScansViaProjection();        // :1534-1538
+    void extractLowDynPointsViaKnnDiff(Session& s, const Cloud& target);   // Session.cpp:393-427
+    void extractHighDynPointsViaKnnDiff(Session& s, const Cloud& target);  // Session.cpp:487-504
+    void removeWeakNDMapPointsHavingStrongNDInNear(Session& s);            // Session.cpp:452-484
+    void detectLowDynamicPoints();               // :1413-1481
+    void updateCurrentMap();                     // :1483-1524
+    void parseUpdatedStaticScansViaProjection(); // :1551-1561
+    void parseLDScansViaProjection();            // :1564-1577
+    void updateScansScanwise();                  // Session.cpp:362-380
+    void runStep0();                             // precleaning + makeGlobalMap (run() :1660-1662)
+    void runStep12();                            // Step 1 + static projection + Step 2 (run() :1665-1669)
+    void runStep3();                             // run() :1672-1675
+};
+
+}  // namespace ltr_oracle
