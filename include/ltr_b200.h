@@ -1,0 +1,164 @@
+/*
+ * ltr_b200.h -- C-ABI of the B200-native LT-removert / LT-map hot path (libltr_b200.so).
+ *
+ * gisbi-kim/lt-mapper exposes no plugin/FFI interface: its surface is the `removert_removert` ROS node
+ * and, inside it, the Removerter::run() call graph (ltremovert/src/Removerter.cpp:1653-1678).  This ABI
+ * is cut at the narrowest data-parallel seam of that call graph -- the per-keyframe loops and the
+ * voxeliser -- so that a host program (ROS/PCL types at its own boundary) keeps the reference's
+ * orchestration and calls these entry points where the reference calls the functions cited below.
+ * Plain pointers and sizes only; no exceptions cross the boundary; every call returns LTR_OK (0) or
+ * a negative ltr_status, with a message retrievable via ltr_last_error().  There is NO CPU fallback:
+ * every entry point fails with LTR_ERR_CUDA if no sm_100 device is usable.
+ *
+ * Conventions
+ *  - Points cross the boundary as AoS float[n][4] = x, y, z, intensity (pcl::PointXYZI payload,
+ *    ltremovert/include/removert/utility.h:90).  On the device they live as SoA.
+ *  - Poses are row-major 4x4 doubles (ltremovert/src/Session.cpp:102-114).  Inverse poses are an INPUT
+ *    (the reference computes them with Eigen::Matrix4d::inverse(), Session.cpp:110) so that every
+ *    implementation shares the same doubles.
+ *  - Handles are small non-negative ints owned by the context; a context is used by one host thread
+ *    at a time and is bound to one GPU.
+ *  - "cloud"   = one flat device point cloud (a map or any merged cloud),
+ *    "scanset" = K per-keyframe clouds stored back to back with K+1 offsets,
+ *    "poses"   = K (pose, inverse pose) pairs.
+ */
+#ifndef LTR_B200_H_
+#define LTR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ltr_ctx ltr_ctx;
+typedef int32_t ltr_cloud;
+typedef int32_t ltr_scanset;
+typedef int32_t ltr_poses;
+
+typedef enum ltr_status {
+    LTR_OK = 0,
+    LTR_ERR_INVALID = -1,      /* bad argument / handle / size (e.g. pose-count != scan-count, Session.cpp:117) */
+    LTR_ERR_CUDA = -2,         /* CUDA runtime failure or no usable sm_100 device */
+    LTR_ERR_UNSUPPORTED = -3,  /* input the reference itself has undefined behaviour on (e.g. 1- or 2-point maps,
+                                  utility.h:158-167 linspace) or outside this build's limits */
+    LTR_ERR_NOMEM = -4
+} ltr_status;
+
+/* ltr_remove_pass modes == the three variants of calcDescrepancyAndParseDynamicPointIdxForEachScan */
+typedef enum ltr_pass_mode {
+    LTR_MODE_HD = 0,  /* scan - map  (Removerter.cpp:542-593; removeOnce / revertOnce) */
+    LTR_MODE_ND = 1,  /* map - scan  (Removerter.cpp:485-540; iremoveOnceForND)        */
+    LTR_MODE_PD = 2   /* scan - map  (Removerter.cpp:429-482; removeOnceForPD)         */
+} ltr_pass_mode;
+
+typedef struct ltr_config {
+    int32_t device;               /* CUDA device ordinal */
+    float vfov_deg, hfov_deg;     /* removert/sequence_vfov, sequence_hfov (RosParamServer.cpp:15-17) */
+    double lidar2base[16];        /* kSE3MatExtrinsicLiDARtoPoseBase (RosParamServer.cpp:28-29), row-major */
+    double base2lidar[16];        /* its inverse (RosParamServer.cpp:30), supplied by the caller */
+    int32_t transform_order;      /* double summation order of pcl::transformPointCloud:
+                                     0 = ((m00 x + m01 y) + m02 z) + m03 (PCL <= 1.9), 1 = ((m03 + m00 x) + m01 y) + m02 z (PCL >= 1.10 SSE2) */
+    int32_t keyframe_batch;       /* keyframes projected per kernel launch (0 = default) */
+    int32_t fast_path;            /* 1 = enable the exactness-preserving fast rejection path (default), 0 = exact arithmetic for every point */
+} ltr_config;
+
+/* Fills cfg with the reference defaults (vfov 50, hfov 360, identity extrinsic, order 0). */
+void ltr_config_default(ltr_config* cfg);
+
+int ltr_create(ltr_ctx** out, const ltr_config* cfg);
+void ltr_destroy(ltr_ctx* ctx);
+const char* ltr_last_error(const ltr_ctx* ctx);  /* valid until the next call on ctx; ctx may be NULL for create errors */
+int ltr_synchronize(ltr_ctx* ctx);
+/* number of kernels of this library launched on ctx so far (for bench.py's gpu_launches) */
+int64_t ltr_kernel_launches(const ltr_ctx* ctx);
+
+/* ---- data movement -------------------------------------------------------------------------- */
+int ltr_cloud_upload(ltr_ctx* ctx, const float* xyzi, int64_t n, ltr_cloud* out);
+int ltr_cloud_size(ltr_ctx* ctx, ltr_cloud c, int64_t* n);
+int ltr_cloud_download(ltr_ctx* ctx, ltr_cloud c, float* xyzi, int64_t capacity, int64_t* n);
+int ltr_cloud_free(ltr_ctx* ctx, ltr_cloud c);
+int ltr_cloud_copy(ltr_ctx* ctx, ltr_cloud src, ltr_cloud* out);               /* "*dst = *src" on pcl clouds */
+int ltr_cloud_concat(ltr_ctx* ctx, ltr_cloud a, ltr_cloud b, ltr_cloud* out);  /* "*a += *b" result (Removerter.cpp:902 etc.) */
+/* Device pointers of the SoA components (x, y, z, intensity), e.g. for a caller-side collective. */
+int ltr_cloud_device_ptrs(ltr_ctx* ctx, ltr_cloud c, float** x, float** y, float** z, float** i, int64_t* n);
+/* Allocates an uninitialised cloud of n points (to be filled through ltr_cloud_device_ptrs). */
+int ltr_cloud_alloc(ltr_ctx* ctx, int64_t n, ltr_cloud* out);
+
+int ltr_scanset_upload(ltr_ctx* ctx, const float* xyzi, const int64_t* offsets /* K+1 */, int32_t K, ltr_scanset* out);
+int ltr_scanset_info(ltr_ctx* ctx, ltr_scanset s, int32_t* K, int64_t* total_points);
+int ltr_scanset_download(ltr_ctx* ctx, ltr_scanset s, float* xyzi, int64_t capacity, int64_t* offsets /* K+1 */);
+int ltr_scanset_free(ltr_ctx* ctx, ltr_scanset s);
+/* Concatenates the clouds of two scansets keyframe by keyframe: out[k] = a[k] ++ b[k] (Session.cpp:370-371). */
+int ltr_scanset_concat_per_keyframe(ltr_ctx* ctx, ltr_scanset a, ltr_scanset b, ltr_scanset* out);
+/* View of all points of a scanset as one flat cloud (copy). */
+int ltr_scanset_flatten(ltr_ctx* ctx, ltr_scanset s, ltr_cloud* out);
+
+int ltr_poses_upload(ltr_ctx* ctx, const double* poses /* K*16 */, const double* inv_poses /* K*16 */, int32_t K, ltr_poses* out);
+int ltr_poses_free(ltr_ctx* ctx, ltr_poses p);
+
+/* ---- hot path ------------------------------------------------------------------------------- */
+
+/* precleaningKeyframes (Session.cpp:506-533): drops points with range < radius and |z| < 0.5. */
+int ltr_preclean(ltr_ctx* ctx, ltr_scanset scans, float radius, ltr_scanset* out);
+
+/* mergeScansWithinGlobalCoordUtil (utility.cpp:170-192; also Session.cpp:186-202, Removerter.cpp:158-177):
+ * out = concat_k pose_k * (lidar2base * scan_k), two-step transform with f32 rounding after each step. */
+int ltr_merge_scans_global(ltr_ctx* ctx, ltr_scanset scans, ltr_poses poses, ltr_cloud* out);
+
+/* octreeDownsampling (utility.cpp:204-219): one centroid per occupied voxel, octree depth-first order. */
+int ltr_voxel_centroid(ltr_ctx* ctx, ltr_cloud in, float leaf, ltr_cloud* out);
+/* Same, applied independently to every keyframe cloud (Session::updateScansScanwise, Session.cpp:374-375). */
+int ltr_voxel_centroid_per_keyframe(ltr_ctx* ctx, ltr_scanset in, float leaf, ltr_scanset* out);
+
+/* One remove / revert / ND / PD pass == calcDescrepancyAndParseDynamicPointIdxForEachScan{,ForND,ForPD}
+ * (Removerter.cpp:542-593, 485-540, 429-482) over the source keyframes [kf_begin, kf_end) of `scans`:
+ * scan range image, two-step map transform, map range image + index image, signed diff, threshold,
+ * union over keyframes.  The result is the per-map-point dynamic flag array kept on the device
+ * (1 = in the reference's dynamic_point_indexes set).  With accumulate != 0 the new flags are OR-ed
+ * into the existing ones of the same map (keyframe-sharded multi-GPU: each rank calls with its own
+ * keyframe range, then the flag arrays are max-reduced across ranks).
+ * n_dynamic (optional) receives the number of flagged points of this context after the pass. */
+int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map, ltr_scanset scans, ltr_poses poses, int32_t kf_begin, int32_t kf_end,
+                    int32_t mode, float res_alpha, float diff_thres, int32_t accumulate, int64_t* n_dynamic);
+/* Device pointer to the N flag bytes of the last ltr_remove_pass on `map` (for an all-reduce hook). */
+int ltr_flags_device_ptr(ltr_ctx* ctx, ltr_cloud map, uint8_t** flags, int64_t* n);
+int ltr_flags_download(ltr_ctx* ctx, ltr_cloud map, uint8_t* flags, int64_t capacity);
+int ltr_flags_upload(ltr_ctx* ctx, ltr_cloud map, const uint8_t* flags, int64_t n);
+/* getStaticIdxFromDynamicIdx + parsePointcloudSubsetUsingPtIdx x2 (Removerter.cpp:675-687, 933-946):
+ * static = unflagged points, dynamic = flagged points, both in ascending map-index order. */
+int ltr_apply_partition(ltr_ctx* ctx, ltr_cloud map, ltr_cloud* out_static, ltr_cloud* out_dynamic);
+
+/* Session::parseScansViaProjection (Session.cpp:348-360) for keyframes [kf_begin, kf_end): project `map`
+ * into each keyframe at res_alpha (reference: kReprojectionAlpha = 3.0) and emit, row-major over pixels,
+ * the nearest map point of every pixel whose winning index != 0 (utility.cpp:74-89), in that keyframe's
+ * LiDAR frame.  out has kf_end - kf_begin keyframes. */
+int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map, ltr_poses poses, int32_t kf_begin, int32_t kf_end, float res_alpha,
+                        ltr_scanset* out);
+
+/* Session::extractLowDynPointsViaKnnDiff / extractHighDynPointsViaKnnDiff (Session.cpp:393-427, 487-504) with
+ * partition{Low,High}DynamicPointsOfScanByKnn (Session.cpp:537-642): every point of keyframe k (poses index
+ * pose_offset + k) is moved to the global frame (as written in the reference: base2lidar first, then the pose),
+ * its k nearest SQUARED distances to `target` are averaged ((float)sum_double / float(k)) and compared with thr;
+ * |avg| < thr -> coexist else diff; both partitions are moved back with global2local.  Either output may be NULL. */
+int ltr_knn_diff(ltr_ctx* ctx, ltr_scanset scans, ltr_poses poses, int32_t pose_offset, ltr_cloud target, int32_t k, float thr,
+                 ltr_scanset* out_coexist, ltr_scanset* out_diff);
+/* Same decision rule for a flat cloud already in the target's frame (no transforms):
+ * Session::removeWeakNDMapPointsHavingStrongNDInNear (Session.cpp:452-484). near = |avg| < thr, far = the rest. */
+int ltr_knn_split_cloud(ltr_ctx* ctx, ltr_cloud query, ltr_cloud target, int32_t k, float thr, ltr_cloud* out_near, ltr_cloud* out_far);
+
+/* ---- introspection for tests / profiling ----------------------------------------------------- */
+/* Evaluates the device restatement of cart2sph + pixel index (utility.cpp:38-56, 118-123) for n points. */
+int ltr_debug_pixel_index(ltr_ctx* ctx, const float* xyz /* n*3 */, int64_t n, int32_t rows, int32_t cols,
+                          int32_t* row, int32_t* col, float* range, float* az, float* el);
+/* resetRimgSize (utility.cpp:222-236) */
+void ltr_reset_rimg_size(float vfov, float hfov, float alpha, int32_t* rows, int32_t* cols);
+/* Statistics of the last ltr_remove_pass / ltr_parse_projected: [0] points projected, [1] taken by the fast path,
+ * [2] sent to the exact path, [3] atomics issued, [4] kernel time in microseconds (CUDA events). */
+int ltr_last_pass_stats(ltr_ctx* ctx, double* stats5);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTR_B200_H_ */

@@ -1,0 +1,388 @@
+// libltr_b200.so -- context, handle tables and data movement of the C-ABI (include/ltr_b200.h).
+#include "ltr_internal.cuh"
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+
+thread_local std::string ltr::g_create_err;
+
+namespace ltr {
+
+int fail(ltr_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+
+int dev_alloc(ltr_ctx* ctx, void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 256;
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? LTR_ERR_NOMEM : LTR_ERR_CUDA, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return LTR_OK;
+}
+void dev_free(ltr_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
+int cloud_new(ltr_ctx* ctx, int64_t n, ltr_cloud* out) {
+    if (n < 0) return fail(ctx, LTR_ERR_INVALID, "negative cloud size");
+    int slot = -1;
+    for (size_t i = 0; i < ctx->clouds.size(); ++i) if (!ctx->clouds[i].used) { slot = (int)i; break; }
+    if (slot < 0) { ctx->clouds.push_back(DevCloud()); slot = (int)ctx->clouds.size() - 1; }
+    DevCloud c;
+    c.n = n; c.cap = round_cap(n); c.used = true;
+    void* p;
+    LTR_TRY(dev_alloc(ctx, &p, (size_t)c.cap * 4 * sizeof(float)));
+    c.base = (float*)p;
+    ctx->clouds[slot] = c;
+    *out = slot;
+    return LTR_OK;
+}
+int cloud_get(ltr_ctx* ctx, ltr_cloud h, DevCloud** c) {
+    if (h < 0 || h >= (int)ctx->clouds.size() || !ctx->clouds[h].used) return fail(ctx, LTR_ERR_INVALID, "invalid cloud handle %d", h);
+    *c = &ctx->clouds[h];
+    return LTR_OK;
+}
+void cloud_release(ltr_ctx* ctx, DevCloud* c) {
+    dev_free(ctx, c->base);
+    dev_free(ctx, c->flags);
+    *c = DevCloud();
+}
+int cloud_ensure_flags(ltr_ctx* ctx, DevCloud* c) {
+    if (c->flags) return LTR_OK;
+    void* p;
+    LTR_TRY(dev_alloc(ctx, &p, (size_t)c->cap));
+    c->flags = (uint8_t*)p;
+    LTR_CUDA(ctx, cudaMemsetAsync(c->flags, 0, (size_t)c->cap, ctx->stream));
+    return LTR_OK;
+}
+int scanset_new(ltr_ctx* ctx, const std::vector<int64_t>& off, ltr_scanset* out) {
+    const int K = (int)off.size() - 1;
+    if (K < 0) return fail(ctx, LTR_ERR_INVALID, "scanset needs K+1 offsets");
+    for (int k = 0; k < K; ++k) if (off[k + 1] < off[k]) return fail(ctx, LTR_ERR_INVALID, "scanset offsets must be non-decreasing");
+    if (off[0] != 0) return fail(ctx, LTR_ERR_INVALID, "scanset offsets must start at 0");
+    int slot = -1;
+    for (size_t i = 0; i < ctx->scansets.size(); ++i) if (!ctx->scansets[i].used) { slot = (int)i; break; }
+    if (slot < 0) { ctx->scansets.push_back(DevScanSet()); slot = (int)ctx->scansets.size() - 1; }
+    DevScanSet s;
+    s.K = K; s.h_off = off; s.used = true;
+    s.pts.n = off[K]; s.pts.cap = round_cap(off[K]); s.pts.used = true;
+    void* p;
+    LTR_TRY(dev_alloc(ctx, &p, (size_t)s.pts.cap * 4 * sizeof(float)));
+    s.pts.base = (float*)p;
+    LTR_TRY(dev_alloc(ctx, &p, (size_t)(K + 1) * sizeof(int64_t)));
+    s.d_off = (int64_t*)p;
+    LTR_CUDA(ctx, cudaMemcpyAsync(s.d_off, off.data(), (size_t)(K + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `off` may be a temporary
+    ctx->scansets[slot] = s;
+    *out = slot;
+    return LTR_OK;
+}
+int scanset_get(ltr_ctx* ctx, ltr_scanset h, DevScanSet** s) {
+    if (h < 0 || h >= (int)ctx->scansets.size() || !ctx->scansets[h].used) return fail(ctx, LTR_ERR_INVALID, "invalid scanset handle %d", h);
+    *s = &ctx->scansets[h];
+    return LTR_OK;
+}
+int poses_get(ltr_ctx* ctx, ltr_poses h, DevPoses** p) {
+    if (h < 0 || h >= (int)ctx->poses.size() || !ctx->poses[h].used) return fail(ctx, LTR_ERR_INVALID, "invalid poses handle %d", h);
+    *p = &ctx->poses[h];
+    return LTR_OK;
+}
+
+// AoS (x,y,z,i) <-> SoA
+__global__ void aos_to_soa_kernel(const float4* __restrict__ in, float* __restrict__ x, float* __restrict__ y, float* __restrict__ z,
+                                  float* __restrict__ w, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = in[i];
+    x[i] = p.x; y[i] = p.y; z[i] = p.z; w[i] = p.w;
+}
+__global__ void soa_to_aos_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                                  const float* __restrict__ w, float4* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = make_float4(x[i], y[i], z[i], w[i]);
+}
+
+static int upload_points(ltr_ctx* ctx, const float* xyzi, DevCloud& c) {
+    if (c.n == 0) return LTR_OK;
+    void* stage;
+    LTR_TRY(dev_alloc(ctx, &stage, (size_t)c.n * 16));
+    LTR_CUDA(ctx, cudaMemcpyAsync(stage, xyzi, (size_t)c.n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    const int T = 256;
+    aos_to_soa_kernel<<<(unsigned)((c.n + T - 1) / T), T, 0, ctx->stream>>>((const float4*)stage, c.x(), c.y(), c.z(), c.i(), c.n);
+    LTR_LAUNCH_CHECK(ctx);
+    dev_free(ctx, stage);
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // caller's host buffer is only read during the call
+    return LTR_OK;
+}
+static int download_points(ltr_ctx* ctx, const DevCloud& c, float* xyzi) {
+    if (c.n == 0) return LTR_OK;
+    void* stage;
+    LTR_TRY(dev_alloc(ctx, &stage, (size_t)c.n * 16));
+    const int T = 256;
+    soa_to_aos_kernel<<<(unsigned)((c.n + T - 1) / T), T, 0, ctx->stream>>>(c.x(), c.y(), c.z(), c.i(), (float4*)stage, c.n);
+    LTR_LAUNCH_CHECK(ctx);
+    LTR_CUDA(ctx, cudaMemcpyAsync(xyzi, stage, (size_t)c.n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    dev_free(ctx, stage);
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LTR_OK;
+}
+
+static bool is_identity(const double* m) {
+    for (int i = 0; i < 16; ++i) if (m[i] != ((i % 5 == 0) ? 1.0 : 0.0)) return false;
+    return true;
+}
+
+}  // namespace ltr
+
+using namespace ltr;
+
+extern "C" {
+
+void ltr_config_default(ltr_config* cfg) {
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->device = 0;
+    cfg->vfov_deg = 50.0f;
+    cfg->hfov_deg = 360.0f;
+    for (int i = 0; i < 16; ++i) cfg->lidar2base[i] = cfg->base2lidar[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    cfg->transform_order = 0;
+    cfg->keyframe_batch = 0;
+    cfg->fast_path = 1;
+}
+
+int ltr_create(ltr_ctx** out, const ltr_config* cfg) {
+    if (!out || !cfg) return fail(nullptr, LTR_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(nullptr, LTR_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, LTR_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, LTR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10) return fail(nullptr, LTR_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    if (!(cfg->vfov_deg > 0) || !(cfg->hfov_deg > 0)) return fail(nullptr, LTR_ERR_INVALID, "fov must be positive");
+    if (cfg->transform_order != 0 && cfg->transform_order != 1) return fail(nullptr, LTR_ERR_INVALID, "transform_order must be 0 or 1");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, LTR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    ltr_ctx* ctx = new ltr_ctx();
+    ctx->cfg = *cfg;
+    if (ctx->cfg.keyframe_batch <= 0) ctx->cfg.keyframe_batch = 32;
+    ctx->device = cfg->device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->ext_identity = is_identity(cfg->lidar2base) && is_identity(cfg->base2lidar);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, LTR_ERR_CUDA, "stream/event creation failed");
+    }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    double ext[24];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) { ext[r * 4 + c] = cfg->base2lidar[r * 4 + c]; ext[12 + r * 4 + c] = cfg->lidar2base[r * 4 + c]; }
+    void* p;
+    if (dev_alloc(ctx, &p, sizeof(ext)) != LTR_OK) { g_create_err = ctx->err; delete ctx; return LTR_ERR_CUDA; }
+    ctx->d_ext = (double*)p;
+    cudaMemcpyAsync(ctx->d_ext, ext, sizeof(ext), cudaMemcpyHostToDevice, ctx->stream);
+    if (dev_alloc(ctx, &p, 8 * sizeof(unsigned long long)) != LTR_OK) { g_create_err = ctx->err; delete ctx; return LTR_ERR_CUDA; }
+    ctx->d_counters = (unsigned long long*)p;
+    cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { delete ctx; return fail(nullptr, LTR_ERR_CUDA, "context initialisation failed"); }
+    *out = ctx;
+    return LTR_OK;
+}
+
+void ltr_destroy(ltr_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& c : ctx->clouds) if (c.used) cloud_release(ctx, &c);
+    for (auto& s : ctx->scansets) if (s.used) { cloud_release(ctx, &s.pts); dev_free(ctx, s.d_off); }
+    for (auto& p : ctx->poses) if (p.used) dev_free(ctx, p.d);
+    dev_free(ctx, ctx->d_ext);
+    dev_free(ctx, ctx->d_counters);
+    cudaStreamSynchronize(ctx->stream);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* ltr_last_error(const ltr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int ltr_synchronize(ltr_ctx* ctx) {
+    if (!ctx) return LTR_ERR_INVALID;
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LTR_OK;
+}
+
+int64_t ltr_kernel_launches(const ltr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ltr_cloud_upload(ltr_ctx* ctx, const float* xyzi, int64_t n, ltr_cloud* out) {
+    if (!ctx || !out || (n > 0 && !xyzi)) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    LTR_TRY(cloud_new(ctx, n, out));
+    return upload_points(ctx, xyzi, ctx->clouds[*out]);
+}
+int ltr_cloud_alloc(ltr_ctx* ctx, int64_t n, ltr_cloud* out) {
+    if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    return cloud_new(ctx, n, out);
+}
+int ltr_cloud_size(ltr_ctx* ctx, ltr_cloud c, int64_t* n) {
+    DevCloud* dc;
+    LTR_TRY(cloud_get(ctx, c, &dc));
+    *n = dc->n;
+    return LTR_OK;
+}
+int ltr_cloud_download(ltr_ctx* ctx, ltr_cloud c, float* xyzi, int64_t capacity, int64_t* n) {
+    DevCloud* dc;
+    LTR_TRY(cloud_get(ctx, c, &dc));
+    if (n) *n = dc->n;
+    if (capacity < dc->n) return fail(ctx, LTR_ERR_INVALID, "download buffer too small (%lld < %lld)", (long long)capacity, (long long)dc->n);
+    return download_points(ctx, *dc, xyzi);
+}
+int ltr_cloud_free(ltr_ctx* ctx, ltr_cloud c) {
+    DevCloud* dc;
+    LTR_TRY(cloud_get(ctx, c, &dc));
+    cloud_release(ctx, dc);
+    return LTR_OK;
+}
+int ltr_cloud_copy(ltr_ctx* ctx, ltr_cloud src, ltr_cloud* out) {
+    DevCloud* s;
+    LTR_TRY(cloud_get(ctx, src, &s));
+    const DevCloud sc = *s;
+    LTR_TRY(cloud_new(ctx, sc.n, out));
+    DevCloud& d = ctx->clouds[*out];
+    if (sc.n > 0) {
+        LTR_CUDA(ctx, cudaMemcpy2DAsync(d.base, (size_t)d.cap * 4, sc.base, (size_t)sc.cap * 4, (size_t)sc.n * 4, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return LTR_OK;
+}
+int ltr_cloud_concat(ltr_ctx* ctx, ltr_cloud a, ltr_cloud b, ltr_cloud* out) {
+    DevCloud *pa, *pb;
+    LTR_TRY(cloud_get(ctx, a, &pa));
+    LTR_TRY(cloud_get(ctx, b, &pb));
+    const DevCloud ca = *pa, cb = *pb;
+    LTR_TRY(cloud_new(ctx, ca.n + cb.n, out));
+    DevCloud& d = ctx->clouds[*out];
+    if (ca.n > 0) LTR_CUDA(ctx, cudaMemcpy2DAsync(d.base, (size_t)d.cap * 4, ca.base, (size_t)ca.cap * 4, (size_t)ca.n * 4, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (cb.n > 0) LTR_CUDA(ctx, cudaMemcpy2DAsync(d.base + ca.n, (size_t)d.cap * 4, cb.base, (size_t)cb.cap * 4, (size_t)cb.n * 4, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    return LTR_OK;
+}
+int ltr_cloud_device_ptrs(ltr_ctx* ctx, ltr_cloud c, float** x, float** y, float** z, float** i, int64_t* n) {
+    DevCloud* dc;
+    LTR_TRY(cloud_get(ctx, c, &dc));
+    if (x) *x = dc->x();
+    if (y) *y = dc->y();
+    if (z) *z = dc->z();
+    if (i) *i = dc->i();
+    if (n) *n = dc->n;
+    return LTR_OK;
+}
+
+int ltr_scanset_upload(ltr_ctx* ctx, const float* xyzi, const int64_t* offsets, int32_t K, ltr_scanset* out) {
+    if (!ctx || !out || !offsets || K < 0) return fail(ctx, LTR_ERR_INVALID, "bad argument");
+    std::vector<int64_t> off(offsets, offsets + K + 1);
+    if (off[K] > 0 && !xyzi) return fail(ctx, LTR_ERR_INVALID, "null points");
+    LTR_TRY(scanset_new(ctx, off, out));
+    return upload_points(ctx, xyzi, ctx->scansets[*out].pts);
+}
+int ltr_scanset_info(ltr_ctx* ctx, ltr_scanset s, int32_t* K, int64_t* total) {
+    DevScanSet* ss;
+    LTR_TRY(scanset_get(ctx, s, &ss));
+    if (K) *K = ss->K;
+    if (total) *total = ss->pts.n;
+    return LTR_OK;
+}
+int ltr_scanset_download(ltr_ctx* ctx, ltr_scanset s, float* xyzi, int64_t capacity, int64_t* offsets) {
+    DevScanSet* ss;
+    LTR_TRY(scanset_get(ctx, s, &ss));
+    if (offsets) std::memcpy(offsets, ss->h_off.data(), (size_t)(ss->K + 1) * sizeof(int64_t));
+    if (!xyzi) return LTR_OK;
+    if (capacity < ss->pts.n) return fail(ctx, LTR_ERR_INVALID, "download buffer too small");
+    return download_points(ctx, ss->pts, xyzi);
+}
+int ltr_scanset_free(ltr_ctx* ctx, ltr_scanset s) {
+    DevScanSet* ss;
+    LTR_TRY(scanset_get(ctx, s, &ss));
+    cloud_release(ctx, &ss->pts);
+    dev_free(ctx, ss->d_off);
+    *ss = DevScanSet();
+    return LTR_OK;
+}
+int ltr_scanset_flatten(ltr_ctx* ctx, ltr_scanset s, ltr_cloud* out) {
+    DevScanSet* ss;
+    LTR_TRY(scanset_get(ctx, s, &ss));
+    const DevCloud sc = ss->pts;
+    LTR_TRY(cloud_new(ctx, sc.n, out));
+    DevCloud& d = ctx->clouds[*out];
+    if (sc.n > 0) LTR_CUDA(ctx, cudaMemcpy2DAsync(d.base, (size_t)d.cap * 4, sc.base, (size_t)sc.cap * 4, (size_t)sc.n * 4, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    return LTR_OK;
+}
+int ltr_scanset_concat_per_keyframe(ltr_ctx* ctx, ltr_scanset a, ltr_scanset b, ltr_scanset* out) {
+    DevScanSet *pa, *pb;
+    LTR_TRY(scanset_get(ctx, a, &pa));
+    LTR_TRY(scanset_get(ctx, b, &pb));
+    if (pa->K != pb->K) return fail(ctx, LTR_ERR_INVALID, "scansets have different keyframe counts (%d vs %d)", pa->K, pb->K);
+    const int K = pa->K;
+    std::vector<int64_t> off((size_t)K + 1, 0);
+    for (int k = 0; k < K; ++k) off[k + 1] = off[k] + (pa->h_off[k + 1] - pa->h_off[k]) + (pb->h_off[k + 1] - pb->h_off[k]);
+    const DevCloud ca = pa->pts, cb = pb->pts;
+    const std::vector<int64_t> oa = pa->h_off, ob = pb->h_off;
+    LTR_TRY(scanset_new(ctx, off, out));
+    DevCloud& d = ctx->scansets[*out].pts;
+    for (int k = 0; k < K; ++k) {
+        const int64_t na = oa[k + 1] - oa[k], nb = ob[k + 1] - ob[k];
+        if (na > 0) LTR_CUDA(ctx, cudaMemcpy2DAsync(d.base + off[k], (size_t)d.cap * 4, ca.base + oa[k], (size_t)ca.cap * 4, (size_t)na * 4, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (nb > 0) LTR_CUDA(ctx, cudaMemcpy2DAsync(d.base + off[k] + na, (size_t)d.cap * 4, cb.base + ob[k], (size_t)cb.cap * 4, (size_t)nb * 4, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return LTR_OK;
+}
+
+int ltr_poses_upload(ltr_ctx* ctx, const double* poses, const double* inv_poses, int32_t K, ltr_poses* out) {
+    if (!ctx || !out || K < 0 || (K > 0 && (!poses || !inv_poses))) return fail(ctx, LTR_ERR_INVALID, "bad argument");
+    int slot = -1;
+    for (size_t i = 0; i < ctx->poses.size(); ++i) if (!ctx->poses[i].used) { slot = (int)i; break; }
+    if (slot < 0) { ctx->poses.push_back(DevPoses()); slot = (int)ctx->poses.size() - 1; }
+    DevPoses p;
+    p.K = K; p.used = true;
+    p.h.resize((size_t)K * 24);
+    for (int k = 0; k < K; ++k) {
+        std::memcpy(&p.h[(size_t)k * 24], inv_poses + (size_t)k * 16, 12 * sizeof(double));
+        std::memcpy(&p.h[(size_t)k * 24 + 12], poses + (size_t)k * 16, 12 * sizeof(double));
+    }
+    void* d;
+    LTR_TRY(dev_alloc(ctx, &d, (size_t)K * 24 * sizeof(double)));
+    p.d = (double*)d;
+    if (K > 0) LTR_CUDA(ctx, cudaMemcpyAsync(p.d, p.h.data(), (size_t)K * 24 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->poses[slot] = p;  // p.h (the source of the async copy) must stay alive: it now lives in the table
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = slot;
+    return LTR_OK;
+}
+int ltr_poses_free(ltr_ctx* ctx, ltr_poses h) {
+    DevPoses* p;
+    LTR_TRY(poses_get(ctx, h, &p));
+    dev_free(ctx, p->d);
+    *p = DevPoses();
+    return LTR_OK;
+}
+
+void ltr_reset_rimg_size(float vfov, float hfov, float alpha, int32_t* rows, int32_t* cols) {
+    // resetRimgSize (utility.cpp:222-236): int = std::round(float * float)
+    *rows = (int32_t)roundf(vfov * alpha);
+    *cols = (int32_t)roundf(hfov * alpha);
+}
+
+int ltr_last_pass_stats(ltr_ctx* ctx, double* s) {
+    if (!ctx || !s) return LTR_ERR_INVALID;
+    for (int i = 0; i < 5; ++i) s[i] = ctx->stats[i];
+    return LTR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// Internal context / device-container definitions shared by the translation units of libltr_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include "../../include/ltr_b200.h"
+
+namespace ltr {
+
+struct DevCloud {
+    float* base = nullptr;      // one allocation: x | y | z | i, each `cap` floats (cap multiple of 64 -> 256 B aligned components)
+    int64_t n = 0, cap = 0;
+    uint8_t* flags = nullptr;   // per-point dynamic flags of the last remove pass (lazily allocated, cap bytes)
+    bool used = false;
+    __host__ __device__ float* x() const { return base; }
+    __host__ __device__ float* y() const { return base + cap; }
+    __host__ __device__ float* z() const { return base + 2 * cap; }
+    __host__ __device__ float* i() const { return base + 3 * cap; }
+};
+
+struct DevScanSet {
+    DevCloud pts;                  // all keyframes back to back
+    std::vector<int64_t> h_off;    // K+1 host offsets
+    int64_t* d_off = nullptr;      // K+1 device offsets
+    int K = 0;
+    bool used = false;
+};
+
+// 24 doubles per keyframe: inverse pose rows 0..2 (12) then pose rows 0..2 (12), row-major 3x4
+struct DevPoses {
+    double* d = nullptr;
+    std::vector<double> h;
+    int K = 0;
+    bool used = false;
+};
+
+struct PtrView { const float *x, *y, *z, *i; int64_t n; };
+
+}  // namespace ltr
+
+struct ltr_ctx {
+    ltr_config cfg;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    std::vector<ltr::DevCloud> clouds;
+    std::vector<ltr::DevScanSet> scansets;
+    std::vector<ltr::DevPoses> poses;
+    int64_t launches = 0;
+    bool ext_identity = true;     // base2lidar/lidar2base exactly identity -> second transform step is exact and skipped
+    double* d_ext = nullptr;      // 24 doubles: base2lidar rows 0..2, lidar2base rows 0..2
+    double stats[5] = {0, 0, 0, 0, 0};
+    unsigned long long* d_counters = nullptr;  // 4 device counters for pass statistics
+};
+
+namespace ltr {
+
+extern thread_local std::string g_create_err;
+
+int fail(ltr_ctx* ctx, int code, const char* fmt, ...);
+
+#define LTR_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) return ::ltr::fail(ctx, LTR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                                                   cudaGetErrorString(e__), __FILE__, __LINE__);     \
+    } while (0)
+
+#define LTR_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != LTR_OK) return rc__; \
+    } while (0)
+
+#define LTR_LAUNCH_CHECK(ctx)                                                                         \
+    do {                                                                                              \
+        (ctx)->launches++;                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                                         \
+        if (e__ != cudaSuccess) return ::ltr::fail(ctx, LTR_ERR_CUDA, "kernel launch failed: %s (%s:%d)", \
+                                                   cudaGetErrorString(e__), __FILE__, __LINE__);      \
+    } while (0)
+
+// allocation helpers (stream-ordered)
+int dev_alloc(ltr_ctx* ctx, void** p, size_t bytes);
+void dev_free(ltr_ctx* ctx, void* p);
+
+int cloud_new(ltr_ctx* ctx, int64_t n, ltr_cloud* out);          // uninitialised cloud of n points
+int cloud_get(ltr_ctx* ctx, ltr_cloud h, DevCloud** c);
+int scanset_new(ltr_ctx* ctx, const std::vector<int64_t>& off, ltr_scanset* out);  // allocates points + uploads offsets
+int scanset_get(ltr_ctx* ctx, ltr_scanset h, DevScanSet** s);
+int poses_get(ltr_ctx* ctx, ltr_poses h, DevPoses** p);
+int cloud_ensure_flags(ltr_ctx* ctx, DevCloud* c);
+void cloud_release(ltr_ctx* ctx, DevCloud* c);
+
+inline int64_t round_cap(int64_t n) { return ((n > 0 ? n : 1) + 63) / 64 * 64; }
+inline PtrView view(const DevCloud& c) { return PtrView{c.x(), c.y(), c.z(), c.i(), c.n}; }
+
+// implemented in util.cu
+int stable_partition_by_flag(ltr_ctx* ctx, const DevCloud& in, const uint8_t* flags, int64_t* n_flagged,
+                             DevCloud* out_unflagged, DevCloud* out_flagged);   // outputs must be pre-allocated with cap >= in.n
+int count_flags(ltr_ctx* ctx, const uint8_t* flags, int64_t n, int64_t* count);
+int exclusive_scan_u32(ltr_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n);  // out[n] elements; returns via out
+int minmax_xyz(ltr_ctx* ctx, const DevCloud& c, float mn[3], float mx[3]);
+int segment_counts(ltr_ctx* ctx, const uint8_t* flags, const DevScanSet& s, std::vector<int64_t>* counts);
+int split_scanset_by_flag(ltr_ctx* ctx, const DevScanSet& in, const uint8_t* flags, ltr_scanset* out_unflagged, ltr_scanset* out_flagged);
+
+}  // namespace ltr

@@ -1,0 +1,331 @@
+// libltr_b200.so -- range-image projection kernels: remove / revert / ND / PD pass and visible-point extraction.
+//
+// Reference functions replaced (paths relative to the lt-mapper repository):
+//   Removerter::scan2RangeImg                                   ltremovert/src/Removerter.cpp:109-156
+//   transformGlobalMapToLocal + map2RangeImg                    ltremovert/src/utility.cpp:64-72, 92-142
+//   range diff + calcDescrepancyAndParseDynamicPointIdx         ltremovert/src/Removerter.cpp:572/459/516, 381-413
+//   calcDescrepancyAndParseDynamicPointIdxForEachScan{,ND,PD}   ltremovert/src/Removerter.cpp:542-593, 485-540, 429-482
+//   parseProjectedPoints / Session::parseScansViaProjection     ltremovert/src/utility.cpp:74-89, ltremovert/src/Session.cpp:348-360
+//
+// Determinism: the reference's per-pixel min is a racy OpenMP loop; its sequential meaning (min range, lowest
+// index among equal ranges) is obtained here with one 64-bit atomicMin on (float_bits(range) << 32 | index).
+#include "ltr_internal.cuh"
+#include "ref_math.cuh"
+#include <algorithm>
+
+namespace ltr {
+
+constexpr uint32_t kNoPointBits = 0x461C4000u;                       // 10000.0f == kFlagNoPOINT (utility.h:93)
+constexpr uint64_t kWinEmpty = ((uint64_t)kNoPointBits << 32);        // (range 10000, index 0) == utility.cpp:103-104
+constexpr uint64_t kWinNone = ~0ull;                                  // "no candidate" for the scan-minus-map variants
+constexpr float kValidDiffUpperBound = 200.0f;                        // utility.h:94
+
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint32_t v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void fill_u64_kernel(uint64_t* __restrict__ p, uint64_t v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__device__ __forceinline__ int find_kf_rel(const int64_t* __restrict__ off, int nb, int64_t i) {
+    int lo = 0, hi = nb;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// scan2RangeImg for the keyframes [kf0, kf0+nb): per-pixel min range via 32-bit atomicMin on the float bits (ranges >= 0).
+__global__ void __launch_bounds__(256) scan_rimg_kernel(PtrView scans, const int64_t* __restrict__ off, int kf0, int nb, ImgShape g,
+                                                        uint32_t* __restrict__ rimg) {
+    const int64_t begin = off[kf0], end = off[kf0 + nb];
+    const int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    const int k = find_kf_rel(off + kf0, nb, i);
+    const Sph s = cart2sph(scans.x[i], scans.y[i], scans.z[i]);
+    int r, c;
+    pixel_index(s, g, &r, &c);
+    atomicMin(&rimg[(size_t)k * g.rows * g.cols + (size_t)r * g.cols + c], __float_as_uint(s.r));
+}
+
+// Exact projection of every map point into every keyframe of the batch.
+//   kCandidatesOnly = true  (HD / revert / PD, diff = scan - map): by monotonicity of f32 subtraction the set
+//       {points with scan - range > thres} is a prefix in range order of the pixel's points, so the pixel winner among
+//       them equals the global pixel winner whenever any exists; only those points touch the atomic.
+//   kCandidatesOnly = false (ND, visible-point extraction): true per-pixel minimum with a read-before-atomic filter.
+template <bool kCandidatesOnly>
+__global__ void __launch_bounds__(256) map_project_kernel(PtrView map, const double* __restrict__ poses, int kf0, int nb,
+                                                          const double* __restrict__ ext, int ext_identity, int order, ImgShape g,
+                                                          const uint32_t* __restrict__ scan_rimg, float thres, uint64_t* __restrict__ win) {
+    extern __shared__ double s_pose[];  // nb * 12: inverse poses of the batch
+    for (int t = threadIdx.x; t < nb * 12; t += blockDim.x) s_pose[t] = poses[(size_t)(kf0 + t / 12) * 24 + (t % 12)];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= map.n) return;
+    const float x = map.x[i], y = map.y[i], z = map.z[i];
+    const size_t npx = (size_t)g.rows * g.cols;
+    for (int k = 0; k < nb; ++k) {
+        float lx, ly, lz;
+        transform_point(s_pose + 12 * k, order, x, y, z, &lx, &ly, &lz);        // utility.cpp:70
+        if (!ext_identity) transform_point(ext, order, lx, ly, lz, &lx, &ly, &lz);  // utility.cpp:71
+        const Sph s = cart2sph(lx, ly, lz);
+        int r, c;
+        pixel_index(s, g, &r, &c);
+        const size_t px = (size_t)k * npx + (size_t)r * g.cols + c;
+        const uint64_t packed = ((uint64_t)__float_as_uint(s.r) << 32) | (uint32_t)i;
+        if (kCandidatesOnly) {
+            const float sr = __uint_as_float(scan_rimg[px]);
+            if (fs(sr, s.r) > thres) atomicMin((unsigned long long*)&win[px], (unsigned long long)packed);
+        } else {
+            if (packed < win[px]) atomicMin((unsigned long long*)&win[px], (unsigned long long)packed);
+        }
+    }
+}
+
+// calcDescrepancyAndParseDynamicPointIdx (Removerter.cpp:381-413) over the batch images; also re-arms `win`.
+template <bool kCandidatesOnly>
+__global__ void __launch_bounds__(256) resolve_kernel(const uint32_t* __restrict__ scan_rimg, uint64_t* __restrict__ win, int64_t total_px,
+                                                      float thres, uint8_t* __restrict__ flags) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total_px) return;
+    const uint64_t w = win[p];
+    if (kCandidatesOnly) {
+        if (w == kWinNone) return;
+        win[p] = kWinNone;
+        const float mr = __uint_as_float((uint32_t)(w >> 32));
+        const float diff = fs(__uint_as_float(scan_rimg[p]), mr);  // scan - map (Removerter.cpp:572, 459)
+        if (diff < kValidDiffUpperBound && diff > thres) flags[(uint32_t)w] = 1;
+    } else {
+        if (w != kWinEmpty) win[p] = kWinEmpty;
+        const float mr = __uint_as_float((uint32_t)(w >> 32));
+        const float diff = fs(mr, __uint_as_float(scan_rimg[p]));  // map - scan (Removerter.cpp:516)
+        if (diff < kValidDiffUpperBound && diff > thres) flags[(uint32_t)w] = 1;
+    }
+}
+
+// parseProjectedPoints (utility.cpp:80-87): row-major scan of the index image, skipping index 0; one block per keyframe.
+__global__ void __launch_bounds__(1024) parse_compact_kernel(uint64_t* __restrict__ win, int npx, uint32_t* __restrict__ list,
+                                                             unsigned int* __restrict__ count) {
+    __shared__ int s_warp[33];
+    __shared__ int s_base;
+    const int k = blockIdx.x;
+    uint64_t* w = win + (size_t)k * npx;
+    uint32_t* out = list + (size_t)k * npx;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int p0 = 0; p0 < npx; p0 += blockDim.x) {
+        const int p = p0 + threadIdx.x;
+        uint32_t idx = 0;
+        if (p < npx) { const uint64_t v = w[p]; idx = (uint32_t)v; if (v != kWinEmpty) w[p] = kWinEmpty; }
+        const bool keep = idx != 0;
+        // block rank
+        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        const int wrank = __popc(b & ((1u << lane) - 1u));
+        if (lane == 0) s_warp[warp] = __popc(b);
+        __syncthreads();
+        if (warp == 0) {
+            const int v = s_warp[lane];
+            int incl = v;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+            s_warp[lane] = incl - v;
+            if (lane == 31) s_warp[32] = incl;
+        }
+        __syncthreads();
+        if (keep) out[s_base + s_warp[warp] + wrank] = idx;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_warp[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count[k] = (unsigned int)s_base;
+}
+
+// emits map_local[ptidx] for every listed index: exact two-step transform of the winning map point
+__global__ void __launch_bounds__(256) parse_emit_kernel(PtrView map, const double* __restrict__ poses, int kf_begin, const int64_t* __restrict__ out_off,
+                                                         int K, const uint32_t* __restrict__ list, int npx, const double* __restrict__ ext,
+                                                         int ext_identity, int order, DevCloud out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= out.n) return;
+    const int k = find_kf_rel(out_off, K, j);
+    const uint32_t idx = list[(size_t)k * npx + (size_t)(j - out_off[k])];
+    float x = map.x[idx], y = map.y[idx], z = map.z[idx];
+    transform_point(poses + (size_t)(kf_begin + k) * 24, order, x, y, z, &x, &y, &z);
+    if (!ext_identity) transform_point(ext, order, x, y, z, &x, &y, &z);
+    out.x()[j] = x; out.y()[j] = y; out.z()[j] = z; out.i()[j] = map.i[idx];
+}
+
+__global__ void debug_pixel_kernel(const float* __restrict__ xyz, int64_t n, ImgShape g, int* __restrict__ row, int* __restrict__ col,
+                                   float* __restrict__ range, float* __restrict__ az, float* __restrict__ el) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Sph s = cart2sph(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    int r, c;
+    pixel_index(s, g, &r, &c);
+    row[i] = r; col[i] = c; range[i] = s.r; az[i] = s.az; el[i] = s.el;
+}
+
+static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, max_blocks));
+}
+
+}  // namespace ltr
+
+using namespace ltr;
+
+extern "C" {
+
+int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_poses poses_h, int32_t kf_begin, int32_t kf_end,
+                    int32_t mode, float res_alpha, float diff_thres, int32_t accumulate, int64_t* n_dynamic) {
+    if (!ctx) return LTR_ERR_INVALID;
+    DevCloud* map;
+    DevScanSet* scans;
+    DevPoses* poses;
+    LTR_TRY(cloud_get(ctx, map_h, &map));
+    LTR_TRY(scanset_get(ctx, scans_h, &scans));
+    LTR_TRY(poses_get(ctx, poses_h, &poses));
+    if (mode != LTR_MODE_HD && mode != LTR_MODE_ND && mode != LTR_MODE_PD) return fail(ctx, LTR_ERR_INVALID, "unknown pass mode %d", mode);
+    if (scans->K != poses->K) return fail(ctx, LTR_ERR_INVALID, "pose count %d != keyframe count %d (Session.cpp:117)", poses->K, scans->K);
+    if (kf_begin < 0 || kf_end > scans->K || kf_begin > kf_end) return fail(ctx, LTR_ERR_INVALID, "keyframe range [%d,%d) outside [0,%d)", kf_begin, kf_end, scans->K);
+    if (map->n >= ((int64_t)1 << 32)) return fail(ctx, LTR_ERR_UNSUPPORTED, "map larger than 2^32 points");
+    int32_t rows, cols;
+    ltr_reset_rimg_size(ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, res_alpha, &rows, &cols);
+    if (rows < 1 || cols < 1) return fail(ctx, LTR_ERR_INVALID, "range image %dx%d is empty (res_alpha %g)", rows, cols, res_alpha);
+    LTR_TRY(cloud_ensure_flags(ctx, map));
+    if (!accumulate && map->n > 0) LTR_CUDA(ctx, cudaMemsetAsync(map->flags, 0, (size_t)map->n, ctx->stream));
+    const ImgShape g{rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg};
+    const int64_t npx = (int64_t)rows * cols;
+    const int B = std::max(1, std::min(ctx->cfg.keyframe_batch, kf_end - kf_begin));
+    const bool cand = (mode != LTR_MODE_ND);
+    LTR_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (map->n > 0 && kf_end > kf_begin) {
+        void *p_rimg, *p_win;
+        LTR_TRY(dev_alloc(ctx, &p_rimg, (size_t)B * npx * sizeof(uint32_t)));
+        LTR_TRY(dev_alloc(ctx, &p_win, (size_t)B * npx * sizeof(uint64_t)));
+        uint32_t* rimg = (uint32_t*)p_rimg;
+        uint64_t* win = (uint64_t*)p_win;
+        const int fill_blocks = ctx->sm_count * 8;
+        fill_u64_kernel<<<grid_for(B * npx, 256, fill_blocks), 256, 0, ctx->stream>>>(win, cand ? kWinNone : kWinEmpty, B * npx);
+        LTR_LAUNCH_CHECK(ctx);
+        for (int k0 = kf_begin; k0 < kf_end; k0 += B) {
+            const int nb = std::min(B, kf_end - k0);
+            fill_u32_kernel<<<grid_for(nb * npx, 256, fill_blocks), 256, 0, ctx->stream>>>(rimg, kNoPointBits, nb * npx);
+            LTR_LAUNCH_CHECK(ctx);
+            const int64_t npts = scans->h_off[k0 + nb] - scans->h_off[k0];
+            if (npts > 0) {
+                scan_rimg_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, k0, nb, g, rimg);
+                LTR_LAUNCH_CHECK(ctx);
+            }
+            const unsigned mb = (unsigned)((map->n + 255) / 256);
+            const size_t smem = (size_t)nb * 12 * sizeof(double);
+            if (cand) map_project_kernel<true><<<mb, 256, smem, ctx->stream>>>(view(*map), poses->d, k0, nb, ctx->d_ext, ctx->ext_identity ? 1 : 0,
+                                                                             ctx->cfg.transform_order, g, rimg, diff_thres, win);
+            else map_project_kernel<false><<<mb, 256, smem, ctx->stream>>>(view(*map), poses->d, k0, nb, ctx->d_ext, ctx->ext_identity ? 1 : 0,
+                                                                          ctx->cfg.transform_order, g, rimg, diff_thres, win);
+            LTR_LAUNCH_CHECK(ctx);
+            const unsigned rb = (unsigned)((nb * npx + 255) / 256);
+            if (cand) resolve_kernel<true><<<rb, 256, 0, ctx->stream>>>(rimg, win, nb * npx, diff_thres, map->flags);
+            else resolve_kernel<false><<<rb, 256, 0, ctx->stream>>>(rimg, win, nb * npx, diff_thres, map->flags);
+            LTR_LAUNCH_CHECK(ctx);
+        }
+        dev_free(ctx, p_rimg);
+        dev_free(ctx, p_win);
+    }
+    LTR_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    if (n_dynamic) LTR_TRY(count_flags(ctx, map->flags, map->n, n_dynamic));
+    LTR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats[0] = (double)map->n * (kf_end - kf_begin);
+    ctx->stats[1] = 0; ctx->stats[2] = ctx->stats[0]; ctx->stats[3] = 0;
+    ctx->stats[4] = (double)ms * 1000.0;
+    return LTR_OK;
+}
+
+int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_t kf_begin, int32_t kf_end, float res_alpha, ltr_scanset* out) {
+    if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    DevCloud* map;
+    DevPoses* poses;
+    LTR_TRY(cloud_get(ctx, map_h, &map));
+    LTR_TRY(poses_get(ctx, poses_h, &poses));
+    if (kf_begin < 0 || kf_end > poses->K || kf_begin > kf_end) return fail(ctx, LTR_ERR_INVALID, "keyframe range [%d,%d) outside [0,%d)", kf_begin, kf_end, poses->K);
+    if (map->n >= ((int64_t)1 << 32)) return fail(ctx, LTR_ERR_UNSUPPORTED, "map larger than 2^32 points");
+    int32_t rows, cols;
+    ltr_reset_rimg_size(ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, res_alpha, &rows, &cols);
+    if (rows < 1 || cols < 1) return fail(ctx, LTR_ERR_INVALID, "range image %dx%d is empty", rows, cols);
+    const ImgShape g{rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg};
+    const int64_t npx = (int64_t)rows * cols;
+    const int K = kf_end - kf_begin;
+    const DevCloud mapc = *map;
+    const DevPoses posc = *poses;
+    std::vector<int64_t> off((size_t)K + 1, 0);
+    LTR_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    void *p_list = nullptr, *p_cnt = nullptr;
+    if (K > 0 && mapc.n > 0) {
+        const int B = std::max(1, std::min(ctx->cfg.keyframe_batch, K));
+        void* p_win;
+        LTR_TRY(dev_alloc(ctx, &p_win, (size_t)B * npx * sizeof(uint64_t)));
+        LTR_TRY(dev_alloc(ctx, &p_list, (size_t)K * npx * sizeof(uint32_t)));
+        LTR_TRY(dev_alloc(ctx, &p_cnt, (size_t)K * sizeof(unsigned int)));
+        uint64_t* win = (uint64_t*)p_win;
+        fill_u64_kernel<<<grid_for(B * npx, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(win, kWinEmpty, B * npx);
+        LTR_LAUNCH_CHECK(ctx);
+        for (int k0 = 0; k0 < K; k0 += B) {
+            const int nb = std::min(B, K - k0);
+            const unsigned mb = (unsigned)((mapc.n + 255) / 256);
+            map_project_kernel<false><<<mb, 256, (size_t)nb * 12 * sizeof(double), ctx->stream>>>(view(mapc), posc.d, kf_begin + k0, nb, ctx->d_ext,
+                ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, nullptr, 0.0f, win);
+            LTR_LAUNCH_CHECK(ctx);
+            parse_compact_kernel<<<nb, 1024, 0, ctx->stream>>>(win, (int)npx, (uint32_t*)p_list + (size_t)k0 * npx, (unsigned int*)p_cnt + k0);
+            LTR_LAUNCH_CHECK(ctx);
+        }
+        dev_free(ctx, p_win);
+        std::vector<unsigned int> cnt((size_t)K);
+        LTR_CUDA(ctx, cudaMemcpyAsync(cnt.data(), p_cnt, (size_t)K * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < K; ++k) off[k + 1] = off[k] + cnt[k];
+    }
+    LTR_TRY(scanset_new(ctx, off, out));
+    DevScanSet& os = ctx->scansets[*out];
+    if (os.pts.n > 0) {
+        parse_emit_kernel<<<(unsigned)((os.pts.n + 255) / 256), 256, 0, ctx->stream>>>(view(mapc), posc.d, kf_begin, os.d_off, K, (const uint32_t*)p_list,
+            (int)npx, ctx->d_ext, ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, os.pts);
+        LTR_LAUNCH_CHECK(ctx);
+    }
+    dev_free(ctx, p_list);
+    dev_free(ctx, p_cnt);
+    LTR_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    LTR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats[0] = (double)mapc.n * K;
+    ctx->stats[1] = 0; ctx->stats[2] = ctx->stats[0]; ctx->stats[3] = 0;
+    ctx->stats[4] = (double)ms * 1000.0;
+    return LTR_OK;
+}
+
+int ltr_debug_pixel_index(ltr_ctx* ctx, const float* xyz, int64_t n, int32_t rows, int32_t cols, int32_t* row, int32_t* col, float* range,
+                          float* az, float* el) {
+    if (!ctx || !xyz || n < 0) return fail(ctx, LTR_ERR_INVALID, "bad argument");
+    if (n == 0) return LTR_OK;
+    void* p;
+    const size_t bytes = (size_t)n * (3 + 5) * 4;
+    LTR_TRY(dev_alloc(ctx, &p, bytes));
+    float* d_xyz = (float*)p;
+    int* d_row = (int*)(d_xyz + 3 * n);
+    int* d_col = d_row + n;
+    float* d_rng = (float*)(d_col + n);
+    float* d_az = d_rng + n;
+    float* d_el = d_az + n;
+    LTR_CUDA(ctx, cudaMemcpyAsync(d_xyz, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    const ImgShape g{rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg};
+    debug_pixel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, g, d_row, d_col, d_rng, d_az, d_el);
+    LTR_LAUNCH_CHECK(ctx);
+    if (row) LTR_CUDA(ctx, cudaMemcpyAsync(row, d_row, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (col) LTR_CUDA(ctx, cudaMemcpyAsync(col, d_col, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (range) LTR_CUDA(ctx, cudaMemcpyAsync(range, d_rng, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (az) LTR_CUDA(ctx, cudaMemcpyAsync(az, d_az, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (el) LTR_CUDA(ctx, cudaMemcpyAsync(el, d_el, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, p);
+    return LTR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,565 @@
+// libltr_b200.so -- order-preserving compaction, reductions, voxel centroid, merge and pre-clean kernels.
+#include "ltr_internal.cuh"
+#include "ref_math.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cfloat>
+#include <cmath>
+#include <algorithm>
+
+namespace ltr {
+
+// ------------------------------------------------------------------------------------------------
+// block-wide rank of a predicate (stable): returns the number of lower-indexed threads with pred set
+// and the block total.  blockDim.x must be a multiple of 32 and <= 1024.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_rank(bool pred, int* total, int* s_warp /* 33 ints */) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const unsigned b = __ballot_sync(0xffffffffu, pred);
+    const int wrank = __popc(b & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(b);
+    __syncthreads();
+    if (warp == 0) {
+        int v = lane < nwarp ? s_warp[lane] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+        s_warp[lane] = incl - v;
+        if (lane == 31) s_warp[32] = incl;
+    }
+    __syncthreads();
+    const int r = s_warp[warp] + wrank;
+    *total = s_warp[32];
+    __syncthreads();
+    return r;
+}
+
+constexpr int kPartThreads = 256;
+constexpr int kPartRounds = 8;
+constexpr int kPartTile = kPartThreads * kPartRounds;
+
+__global__ void __launch_bounds__(kPartThreads) part_count_kernel(const uint8_t* __restrict__ flags, int64_t n, uint32_t* __restrict__ block_cnt) {
+    __shared__ int s_warp[33];
+    const int64_t base = (int64_t)blockIdx.x * kPartTile;
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < kPartRounds; ++r) {
+        const int64_t i = base + (int64_t)r * kPartThreads + threadIdx.x;
+        cnt += (i < n && flags[i]) ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kPartThreads / 32; ++w) t += s_warp[w];
+        block_cnt[blockIdx.x] = (uint32_t)t;
+    }
+}
+
+// single-block exclusive scan of up to 2^31 total over nb block counts; writes total to out[nb]
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int nb) {
+    __shared__ int s_warp[33];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += 1024) {
+        const int i = b0 + threadIdx.x;
+        const uint32_t v = i < nb ? in[i] : 0u;
+        // inclusive warp scan
+        uint32_t incl = v;
+        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+        if (lane == 31) s_warp[warp] = (int)incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+            int wi = w;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if ((int)lane >= o) wi += t; }
+            s_warp[lane] = wi - w;
+            if (lane == 31) s_warp[32] = wi;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + (uint32_t)s_warp[warp] + incl - v;
+        if (i < nb) out[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += (uint32_t)s_warp[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[nb] = s_carry;
+}
+
+__global__ void __launch_bounds__(kPartThreads) part_scatter_kernel(PtrView in, const uint8_t* __restrict__ flags,
+                                                                    const uint32_t* __restrict__ block_off, DevCloud out0, DevCloud out1) {
+    __shared__ int s_warp[33];
+    const int64_t base = (int64_t)blockIdx.x * kPartTile;
+    int64_t dyn_before = block_off[blockIdx.x];
+#pragma unroll 1
+    for (int r = 0; r < kPartRounds; ++r) {
+        const int64_t i = base + (int64_t)r * kPartThreads + threadIdx.x;
+        const bool valid = i < in.n;
+        const bool f = valid && flags[i];
+        int total;
+        const int rk = block_rank(f, &total, s_warp);
+        if (valid) {
+            const float x = in.x[i], y = in.y[i], z = in.z[i], w = in.i[i];
+            if (f) {
+                const int64_t o = dyn_before + rk;
+                out1.x()[o] = x; out1.y()[o] = y; out1.z()[o] = z; out1.i()[o] = w;
+            } else {
+                const int64_t o = i - (dyn_before + rk);
+                out0.x()[o] = x; out0.y()[o] = y; out0.z()[o] = z; out0.i()[o] = w;
+            }
+        }
+        dyn_before += total;
+    }
+}
+
+int stable_partition_by_flag(ltr_ctx* ctx, const DevCloud& in, const uint8_t* flags, int64_t* n_flagged, DevCloud* out0, DevCloud* out1) {
+    const int64_t n = in.n;
+    if (n == 0) { *n_flagged = 0; out0->n = 0; out1->n = 0; return LTR_OK; }
+    const int nb = (int)((n + kPartTile - 1) / kPartTile);
+    void* p;
+    LTR_TRY(dev_alloc(ctx, &p, (size_t)(2 * nb + 2) * sizeof(uint32_t)));
+    uint32_t* cnt = (uint32_t*)p;
+    uint32_t* off = cnt + nb;
+    part_count_kernel<<<nb, kPartThreads, 0, ctx->stream>>>(flags, n, cnt);
+    LTR_LAUNCH_CHECK(ctx);
+    scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, off, nb);
+    LTR_LAUNCH_CHECK(ctx);
+    part_scatter_kernel<<<nb, kPartThreads, 0, ctx->stream>>>(view(in), flags, off, *out0, *out1);
+    LTR_LAUNCH_CHECK(ctx);
+    uint32_t total = 0;
+    LTR_CUDA(ctx, cudaMemcpyAsync(&total, off + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, p);
+    *n_flagged = total;
+    out1->n = total;
+    out0->n = n - total;
+    return LTR_OK;
+}
+
+int count_flags(ltr_ctx* ctx, const uint8_t* flags, int64_t n, int64_t* count) {
+    if (n == 0) { *count = 0; return LTR_OK; }
+    const int nb = (int)((n + kPartTile - 1) / kPartTile);
+    void* p;
+    LTR_TRY(dev_alloc(ctx, &p, (size_t)(2 * nb + 2) * sizeof(uint32_t)));
+    uint32_t* cnt = (uint32_t*)p;
+    part_count_kernel<<<nb, kPartThreads, 0, ctx->stream>>>(flags, n, cnt);
+    LTR_LAUNCH_CHECK(ctx);
+    scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, cnt + nb, nb);
+    LTR_LAUNCH_CHECK(ctx);
+    uint32_t total = 0;
+    LTR_CUDA(ctx, cudaMemcpyAsync(&total, cnt + 2 * nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, p);
+    *count = total;
+    return LTR_OK;
+}
+
+int exclusive_scan_u32(ltr_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n) {
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, n, ctx->stream);
+    void* tmp;
+    LTR_TRY(dev_alloc(ctx, &tmp, tmp_bytes));
+    LTR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, n, ctx->stream));
+    ctx->launches += 2;
+    dev_free(ctx, tmp);
+    return LTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// min / max of x, y, z (pcl::getMinMax3D inside OctreePointCloud::defineBoundingBox)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+static inline float ord2f(uint32_t o) {
+    const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    float f; memcpy(&f, &u, 4); return f;
+}
+
+__global__ void __launch_bounds__(256) minmax_kernel(PtrView c, uint32_t* __restrict__ out /* 6: min xyz, max xyz (ordered encoding) */) {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = c.x[i], y = c.y[i], z = c.z[i];
+        mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+        mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+    }
+    for (int d = 0; d < 3; ++d)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_down_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_down_sync(0xffffffffu, mx[d], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int d = 0; d < 3; ++d) { atomicMin(&out[d], f2ord(mn[d])); atomicMax(&out[3 + d], f2ord(mx[d])); }
+}
+
+static int minmax_view(ltr_ctx* ctx, const PtrView& v, float mn[3], float mx[3]) {
+    void* p;
+    LTR_TRY(dev_alloc(ctx, &p, 6 * sizeof(uint32_t)));
+    uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    LTR_CUDA(ctx, cudaMemcpyAsync(p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    const int blocks = (int)std::min<int64_t>((v.n + 255) / 256, (int64_t)ctx->sm_count * 8);
+    minmax_kernel<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(v, (uint32_t*)p);
+    LTR_LAUNCH_CHECK(ctx);
+    uint32_t res[6];
+    LTR_CUDA(ctx, cudaMemcpyAsync(res, p, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, p);
+    for (int d = 0; d < 3; ++d) { mn[d] = ord2f(res[d]); mx[d] = ord2f(res[3 + d]); }
+    return LTR_OK;
+}
+
+int minmax_xyz(ltr_ctx* ctx, const DevCloud& c, float mn[3], float mx[3]) { return minmax_view(ctx, view(c), mn, mx); }
+
+// ------------------------------------------------------------------------------------------------
+// Voxel centroid == pcl::octree::OctreePointCloudVoxelCentroid as used by octreeDownsampling
+// (ltremovert/src/utility.cpp:204-219).  PCL semantics (published PCL 1.10 sources):
+//   bounding box from min/max (max padded by 512*FLT_EPSILON in f32), grown to a cube of side
+//   2^depth*res and centred; key = (unsigned)(((double)p - min) / res); centroid = f32 sums in
+//   insertion order / (float)count; output order = octree DFS = ascending Morton code with x as the
+//   most significant bit of each level.
+// GPU: key -> 3*depth-bit Morton code -> stable LSD radix sort (code, index) -> run heads -> one thread
+// per voxel sums its run sequentially in original index order (bit-exact f32 sums).
+// ------------------------------------------------------------------------------------------------
+struct VoxBox { double min[3]; double res; int depth; };
+
+static VoxBox define_box(const float mn[3], const float mx[3], float leaf) {
+    // OctreePointCloud::defineBoundingBox() + getKeyBitSize()
+    VoxBox b;
+    b.res = (double)leaf;
+    const float pad = FLT_EPSILON * 512.0f;
+    const float eps = FLT_EPSILON;
+    double lo[3], hi[3];
+    unsigned mk[3];
+    for (int d = 0; d < 3; ++d) {
+        const float hf = mx[d] + pad;  // float add
+        lo[d] = (double)mn[d];
+        hi[d] = (double)hf;
+        const double a = std::min(lo[d], hi[d]);
+        const double c = std::max(a, hi[d]);
+        lo[d] = a; hi[d] = c;
+        mk[d] = (unsigned)std::ceil((hi[d] - lo[d] - eps) / b.res);
+    }
+    const unsigned max_voxels = std::max(std::max(std::max(mk[0], mk[1]), mk[2]), 2u);
+    const double lg = std::log((double)max_voxels) / std::log(2.0);
+    b.depth = (int)std::max(std::min(32u, (unsigned)std::ceil(lg - eps)), 0u);
+    const double side = (double)(1u << b.depth) * b.res;
+    for (int d = 0; d < 3; ++d) {
+        const double over = (side - (hi[d] - lo[d])) / 2.0;
+        if (over > eps) { lo[d] -= over; hi[d] += over; }
+        b.min[d] = lo[d];
+    }
+    return b;
+}
+
+__device__ __forceinline__ uint64_t spread3(uint32_t v) {  // 21 bits -> every third bit
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) vox_key_kernel(PtrView c, VoxBox b, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx,
+                                                      unsigned int* __restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    const double fx = __ddiv_rn(__dsub_rn((double)c.x[i], b.min[0]), b.res);
+    const double fy = __ddiv_rn(__dsub_rn((double)c.y[i], b.min[1]), b.res);
+    const double fz = __ddiv_rn(__dsub_rn((double)c.z[i], b.min[2]), b.res);
+    const double lim = (double)(1u << b.depth);
+    if (!(fx >= 0.0 && fy >= 0.0 && fz >= 0.0 && fx < lim && fy < lim && fz < lim)) atomicAdd(bad, 1u);
+    const uint32_t kx = (uint32_t)__double2uint_rz(fx), ky = (uint32_t)__double2uint_rz(fy), kz = (uint32_t)__double2uint_rz(fz);
+    keys[i] = (spread3(kx) << 2) | (spread3(ky) << 1) | spread3(kz);
+    idx[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) vox_head_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ head) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+// one thread per voxel: find its run [start, end) and sum sequentially in sorted (== insertion) order
+__global__ void __launch_bounds__(256) vox_centroid_kernel(PtrView c, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idx,
+                                                           const uint32_t* __restrict__ head, const uint32_t* __restrict__ rank, int64_t n,
+                                                           DevCloud out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !head[i]) return;
+    const uint64_t key = keys[i];
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f, si = 0.0f;
+    int64_t j = i;
+    int cnt = 0;
+    do {
+        const uint32_t p = idx[j];
+        sx = fa(sx, c.x[p]); sy = fa(sy, c.y[p]); sz = fa(sz, c.z[p]); si = fa(si, c.i[p]);
+        ++cnt; ++j;
+    } while (j < n && keys[j] == key);
+    const float fc = (float)cnt;
+    const uint32_t o = rank[i];
+    out.x()[o] = fd(sx, fc); out.y()[o] = fd(sy, fc); out.z()[o] = fd(sz, fc); out.i()[o] = fd(si, fc);
+}
+
+// `out` must be allocated with cap >= in.n; sets out->n
+static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out) {
+    const int64_t n = v.n;
+    if (n == 0) { out->n = 0; return LTR_OK; }
+    if (!(leaf > 0.0f)) return fail(ctx, LTR_ERR_INVALID, "voxel leaf must be positive");
+    if (n >= (int64_t)1 << 31) return fail(ctx, LTR_ERR_UNSUPPORTED, "cloud too large for voxel centroid");
+    float mn[3], mx[3];
+    LTR_TRY(minmax_view(ctx, v, mn, mx));
+    const VoxBox b = define_box(mn, mx, leaf);
+    if (b.depth > 21) return fail(ctx, LTR_ERR_UNSUPPORTED, "octree depth %d > 21 (extent/leaf too large)", b.depth);
+    void* p;
+    const size_t kb = (size_t)n * sizeof(uint64_t), ib = (size_t)n * sizeof(uint32_t);
+    LTR_TRY(dev_alloc(ctx, &p, 2 * kb + 4 * ib + 256));
+    uint64_t* keys0 = (uint64_t*)p;
+    uint64_t* keys1 = keys0 + n;
+    uint32_t* idx0 = (uint32_t*)(keys1 + n);
+    uint32_t* idx1 = idx0 + n;
+    uint32_t* head = idx1 + n;
+    uint32_t* rank = head + n;
+    unsigned int* bad = (unsigned int*)(rank + n);
+    LTR_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(unsigned int), ctx->stream));
+    const int T = 256;
+    const unsigned nb = (unsigned)((n + T - 1) / T);
+    vox_key_kernel<<<nb, T, 0, ctx->stream>>>(v, b, keys0, idx0, bad);
+    LTR_LAUNCH_CHECK(ctx);
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys0, keys1, idx0, idx1, (int)n, 0, 3 * b.depth, ctx->stream);
+    void* tmp;
+    LTR_TRY(dev_alloc(ctx, &tmp, tmp_bytes));
+    LTR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys0, keys1, idx0, idx1, (int)n, 0, 3 * b.depth, ctx->stream));
+    ctx->launches += (3 * b.depth + 7) / 8 + 1;
+    dev_free(ctx, tmp);
+    vox_head_kernel<<<nb, T, 0, ctx->stream>>>(keys1, n, head);
+    LTR_LAUNCH_CHECK(ctx);
+    LTR_TRY(exclusive_scan_u32(ctx, head, rank, n));
+    vox_centroid_kernel<<<nb, T, 0, ctx->stream>>>(v, keys1, idx1, head, rank, n, *out);
+    LTR_LAUNCH_CHECK(ctx);
+    uint32_t last[2];
+    unsigned int hbad = 0;
+    LTR_CUDA(ctx, cudaMemcpyAsync(&last[0], rank + n - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaMemcpyAsync(&last[1], head + n - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaMemcpyAsync(&hbad, bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, p);
+    if (hbad) return fail(ctx, LTR_ERR_UNSUPPORTED, "%u points fall outside the octree bounding box (non-finite coordinates?)", hbad);
+    out->n = (int64_t)last[0] + last[1];
+    return LTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mergeScansWithinGlobalCoordUtil (utility.cpp:170-192): local -> lidar2base -> pose, f32 rounding after each step
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_kf(const int64_t* __restrict__ off, int K, int64_t i) {
+    int lo = 0, hi = K;  // off[lo] <= i < off[hi]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) merge_global_kernel(PtrView in, const int64_t* __restrict__ off, int K, const double* __restrict__ poses,
+                                                           const double* __restrict__ ext, int ext_identity, int order, DevCloud out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    const int k = find_kf(off, K, i);
+    float x = in.x[i], y = in.y[i], z = in.z[i];
+    if (!ext_identity) transform_point(ext + 12, order, x, y, z, &x, &y, &z);  // lidar2base
+    transform_point(poses + (size_t)k * 24 + 12, order, x, y, z, &x, &y, &z);  // pose
+    out.x()[i] = x; out.y()[i] = y; out.z()[i] = z; out.i()[i] = in.i[i];
+}
+
+// precleaningKeyframes (Session.cpp:506-533)
+__global__ void __launch_bounds__(256) preclean_flag_kernel(PtrView in, float radius, uint8_t* __restrict__ drop) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    const float x = in.x[i], y = in.y[i], z = in.z[i];
+    const float r = __fsqrt_rn(fa(fa(fm(x, x), fm(y, y)), fm(z, z)));
+    drop[i] = (r < radius && (double)z < 0.5 && -0.5 < (double)z) ? 1 : 0;
+}
+
+__global__ void segment_count_kernel(const uint8_t* __restrict__ flags, const int64_t* __restrict__ off, int K, unsigned long long* __restrict__ cnt) {
+    const int k = blockIdx.x;
+    if (k >= K) return;
+    unsigned long long c = 0;
+    for (int64_t i = off[k] + threadIdx.x; i < off[k + 1]; i += blockDim.x) c += flags[i] ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt[k], c);
+}
+
+// per-keyframe counts of set flags -> host vector
+int segment_counts(ltr_ctx* ctx, const uint8_t* flags, const DevScanSet& s, std::vector<int64_t>* counts) {
+    counts->assign((size_t)s.K, 0);
+    if (s.K == 0) return LTR_OK;
+    void* p;
+    LTR_TRY(dev_alloc(ctx, &p, (size_t)s.K * sizeof(unsigned long long)));
+    LTR_CUDA(ctx, cudaMemsetAsync(p, 0, (size_t)s.K * sizeof(unsigned long long), ctx->stream));
+    segment_count_kernel<<<s.K, 256, 0, ctx->stream>>>(flags, s.d_off, s.K, (unsigned long long*)p);
+    LTR_LAUNCH_CHECK(ctx);
+    std::vector<unsigned long long> h((size_t)s.K);
+    LTR_CUDA(ctx, cudaMemcpyAsync(h.data(), p, (size_t)s.K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, p);
+    for (int k = 0; k < s.K; ++k) (*counts)[k] = (int64_t)h[k];
+    return LTR_OK;
+}
+
+// Splits a scanset by per-point flags into (unflagged, flagged) scansets, order preserved inside each keyframe.
+int split_scanset_by_flag(ltr_ctx* ctx, const DevScanSet& in_ref, const uint8_t* flags, ltr_scanset* out_unflagged, ltr_scanset* out_flagged) {
+    const DevScanSet in = in_ref;  // copy: the handle table may be reallocated by scanset_new
+    std::vector<int64_t> cnt;
+    LTR_TRY(segment_counts(ctx, flags, in, &cnt));
+    std::vector<int64_t> off0((size_t)in.K + 1, 0), off1((size_t)in.K + 1, 0);
+    for (int k = 0; k < in.K; ++k) {
+        off1[k + 1] = off1[k] + cnt[k];
+        off0[k + 1] = off0[k] + (in.h_off[k + 1] - in.h_off[k]) - cnt[k];
+    }
+    ltr_scanset h0, h1;
+    const DevCloud src = in.pts;  // copy: the table may be reallocated by scanset_new
+    LTR_TRY(scanset_new(ctx, off0, &h0));
+    LTR_TRY(scanset_new(ctx, off1, &h1));
+    // a global stable partition keeps keyframe order, so it lands exactly at the per-keyframe offsets
+    DevCloud o0 = ctx->scansets[h0].pts, o1 = ctx->scansets[h1].pts;
+    if (src.n > 0) {
+        // outputs may be smaller than src.n in capacity only by construction of sizes: they are exact
+        int64_t nf = 0;
+        LTR_TRY(stable_partition_by_flag(ctx, src, flags, &nf, &o0, &o1));
+        if (nf != off1[in.K]) return fail(ctx, LTR_ERR_CUDA, "internal: partition count mismatch");
+    }
+    if (out_unflagged) *out_unflagged = h0; else ltr_scanset_free(ctx, h0);
+    if (out_flagged) *out_flagged = h1; else ltr_scanset_free(ctx, h1);
+    return LTR_OK;
+}
+
+}  // namespace ltr
+
+using namespace ltr;
+
+extern "C" {
+
+int ltr_voxel_centroid(ltr_ctx* ctx, ltr_cloud in, float leaf, ltr_cloud* out) {
+    if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    DevCloud* c;
+    LTR_TRY(cloud_get(ctx, in, &c));
+    const DevCloud src = *c;
+    LTR_TRY(cloud_new(ctx, src.n, out));
+    DevCloud o = ctx->clouds[*out];
+    const int rc = voxel_view(ctx, view(src), leaf, &o);
+    if (rc != LTR_OK) { cloud_release(ctx, &ctx->clouds[*out]); return rc; }
+    ctx->clouds[*out].n = o.n;
+    return LTR_OK;
+}
+
+int ltr_voxel_centroid_per_keyframe(ltr_ctx* ctx, ltr_scanset in, float leaf, ltr_scanset* out) {
+    if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    DevScanSet* s;
+    LTR_TRY(scanset_get(ctx, in, &s));
+    const DevCloud src = s->pts;
+    const std::vector<int64_t> off = s->h_off;
+    const int K = s->K;
+    // worst case every point survives: voxelise into a scratch of the input layout, then compact
+    ltr_cloud scratch;
+    LTR_TRY(cloud_new(ctx, src.n, &scratch));
+    const DevCloud sc = ctx->clouds[scratch];
+    std::vector<int64_t> noff((size_t)K + 1, 0);
+    for (int k = 0; k < K; ++k) {
+        PtrView v{src.x() + off[k], src.y() + off[k], src.z() + off[k], src.i() + off[k], off[k + 1] - off[k]};
+        DevCloud o = sc;
+        o.base = sc.base + off[k];  // component stride stays sc.cap
+        const int rc = voxel_view(ctx, v, leaf, &o);
+        if (rc != LTR_OK) { ltr_cloud_free(ctx, scratch); return rc; }
+        noff[k + 1] = noff[k] + o.n;
+    }
+    LTR_TRY(scanset_new(ctx, noff, out));
+    DevCloud& d = ctx->scansets[*out].pts;
+    for (int k = 0; k < K; ++k) {
+        const int64_t m = noff[k + 1] - noff[k];
+        if (m > 0) LTR_CUDA(ctx, cudaMemcpy2DAsync(d.base + noff[k], (size_t)d.cap * 4, sc.base + off[k], (size_t)sc.cap * 4, (size_t)m * 4, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ltr_cloud_free(ctx, scratch);
+    return LTR_OK;
+}
+
+int ltr_merge_scans_global(ltr_ctx* ctx, ltr_scanset scans, ltr_poses poses, ltr_cloud* out) {
+    if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    DevScanSet* s;
+    DevPoses* p;
+    LTR_TRY(scanset_get(ctx, scans, &s));
+    LTR_TRY(poses_get(ctx, poses, &p));
+    if (p->K != s->K) return fail(ctx, LTR_ERR_INVALID, "pose count %d != keyframe count %d (Session.cpp:117)", p->K, s->K);
+    const DevScanSet ss = *s;
+    const DevPoses pp = *p;
+    LTR_TRY(cloud_new(ctx, ss.pts.n, out));
+    if (ss.pts.n == 0) return LTR_OK;
+    const int T = 256;
+    merge_global_kernel<<<(unsigned)((ss.pts.n + T - 1) / T), T, 0, ctx->stream>>>(view(ss.pts), ss.d_off, ss.K, pp.d, ctx->d_ext,
+                                                                                ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, ctx->clouds[*out]);
+    LTR_LAUNCH_CHECK(ctx);
+    return LTR_OK;
+}
+
+int ltr_preclean(ltr_ctx* ctx, ltr_scanset scans, float radius, ltr_scanset* out) {
+    if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    DevScanSet* s;
+    LTR_TRY(scanset_get(ctx, scans, &s));
+    const DevScanSet ss = *s;
+    void* drop;
+    LTR_TRY(dev_alloc(ctx, &drop, (size_t)std::max<int64_t>(ss.pts.n, 1)));
+    if (ss.pts.n > 0) {
+        const int T = 256;
+        preclean_flag_kernel<<<(unsigned)((ss.pts.n + T - 1) / T), T, 0, ctx->stream>>>(view(ss.pts), radius, (uint8_t*)drop);
+        LTR_LAUNCH_CHECK(ctx);
+    }
+    const int rc = split_scanset_by_flag(ctx, ss, (const uint8_t*)drop, out, nullptr);
+    dev_free(ctx, drop);
+    return rc;
+}
+
+int ltr_flags_device_ptr(ltr_ctx* ctx, ltr_cloud map, uint8_t** flags, int64_t* n) {
+    DevCloud* c;
+    LTR_TRY(cloud_get(ctx, map, &c));
+    LTR_TRY(cloud_ensure_flags(ctx, c));
+    if (flags) *flags = c->flags;
+    if (n) *n = c->n;
+    return LTR_OK;
+}
+int ltr_flags_download(ltr_ctx* ctx, ltr_cloud map, uint8_t* flags, int64_t capacity) {
+    DevCloud* c;
+    LTR_TRY(cloud_get(ctx, map, &c));
+    LTR_TRY(cloud_ensure_flags(ctx, c));
+    if (capacity < c->n) return fail(ctx, LTR_ERR_INVALID, "flag buffer too small");
+    if (c->n > 0) LTR_CUDA(ctx, cudaMemcpyAsync(flags, c->flags, (size_t)c->n, cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LTR_OK;
+}
+int ltr_flags_upload(ltr_ctx* ctx, ltr_cloud map, const uint8_t* flags, int64_t n) {
+    DevCloud* c;
+    LTR_TRY(cloud_get(ctx, map, &c));
+    if (n != c->n) return fail(ctx, LTR_ERR_INVALID, "flag count %lld != map size %lld", (long long)n, (long long)c->n);
+    LTR_TRY(cloud_ensure_flags(ctx, c));
+    if (n > 0) LTR_CUDA(ctx, cudaMemcpyAsync(c->flags, flags, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LTR_OK;
+}
+
+int ltr_apply_partition(ltr_ctx* ctx, ltr_cloud map, ltr_cloud* out_static, ltr_cloud* out_dynamic) {
+    if (!ctx || !out_static || !out_dynamic) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    DevCloud* c;
+    LTR_TRY(cloud_get(ctx, map, &c));
+    // getStaticIdxFromDynamicIdx builds linspace<int>(0, N, N) (utility.h:158-167): integer step N/(N-1) is 1 only for
+    // N >= 3; N == 1 divides by zero and N == 2 indexes out of range in the reference.
+    if (c->n == 1 || c->n == 2) return fail(ctx, LTR_ERR_UNSUPPORTED, "maps of 1 or 2 points hit undefined behaviour in the reference (utility.h:158-167)");
+    LTR_TRY(cloud_ensure_flags(ctx, c));
+    const DevCloud src = *c;
+    LTR_TRY(cloud_new(ctx, src.n, out_static));
+    LTR_TRY(cloud_new(ctx, src.n, out_dynamic));
+    DevCloud o0 = ctx->clouds[*out_static], o1 = ctx->clouds[*out_dynamic];
+    int64_t nf = 0;
+    LTR_TRY(stable_partition_by_flag(ctx, src, src.flags, &nf, &o0, &o1));
+    ctx->clouds[*out_static].n = o0.n;
+    ctx->clouds[*out_dynamic].n = o1.n;
+    return LTR_OK;
+}
+
+}  // extern "C"
