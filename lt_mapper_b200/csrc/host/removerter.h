@@ -1,0 +1,105 @@
+// Host-side mirror of ltremovert::Removerter / ltremovert::Session (reference: ltremovert/include/removert/
+// Removerter.h:9-204, Session.h:9-136).  Same member and method names, same statement order as
+// ltremovert/src/Removerter.cpp / Session.cpp; every cloud is a device handle of the C-ABI in include/ltr_b200.h
+// and every loop over keyframes or points is one C-ABI call.  Plain C++17, no CUDA, no ROS/PCL: a ROS build would
+// convert pcl::PointCloud<PointXYZI> to/from the float[n][4] arrays at load/save time only.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../../include/ltr_removert.h"
+
+namespace ltremovert_b200 {
+
+struct PassLog { std::string what; int64_t n_map, n_dynamic, n_static_after, n_dynamic_after; };
+
+class Removerter;
+
+class Session {
+public:
+    static constexpr float kReprojectionAlpha = 3.0f;  // Session.h:13
+    std::string sess_type_;
+    int num_keyframes_ = 0;                            // this rank's keyframes
+    ltr_poses keyframe_poses_ = -1;                    // keyframe_poses_ + keyframe_inverse_poses_ (Session.h:36-37)
+    // per-keyframe clouds (Session.h:40-56)
+    ltr_scanset keyframe_scans_ = -1, keyframe_scans_static_projected_ = -1, keyframe_scans_dynamic_ = -1;
+    ltr_scanset scans_knn_coexist_ = -1, scans_knn_diff_ = -1;
+    ltr_scanset keyframe_scans_updated_ = -1, keyframe_scans_updated_strong_ = -1, keyframe_scans_pd_ = -1,
+                keyframe_scans_strong_pd_ = -1, keyframe_scans_strong_nd_ = -1, keyframe_scans_weak_nd_ = -1;
+    // maps (Session.h:67-87)
+    ltr_cloud map_global_orig_ = -1, map_global_curr_ = -1, map_global_curr_static_ = -1, map_global_curr_dynamic_ = -1;
+    ltr_cloud map_global_updated_ = -1, map_global_updated_strong_ = -1;
+    ltr_cloud map_global_nd_ = -1, map_global_nd_strong_ = -1, map_global_nd_weak_ = -1;
+    ltr_cloud map_global_pd_ = -1, map_global_pd_orig_ = -1, map_global_pd_strong_ = -1, map_global_pd_weak_ = -1;
+
+    std::map<std::string, ltr_cloud*> cloud_names();
+    std::map<std::string, ltr_scanset*> scanset_names();
+};
+
+class Removerter {
+public:
+    explicit Removerter(const ltrh_params& p);
+    ~Removerter();
+    int init();  // creates the device context; returns ltr_status
+
+    // ---- reference call graph (Removerter.cpp) ----
+    int precleaningKeyframes(float radius);                                    // :102-106 -> Session.cpp:506-533
+    int makeGlobalMap();                                                       // :248-252
+    int makeGlobalMap(Session& s);                                             // :213-245
+    int removeOnce(Session& target, Session& source, float res);               // :882-905
+    int revertOnce(Session& target, Session& source, float res);               // :908-931
+    int iremoveOnceForND(Session& target, Session& source, float res);         // :831-854
+    int removeOnceForPD(Session& target, Session& source, float res);          // :856-880
+    int resetCurrrentMapAsDynamic(Session& s, bool as_dynamic);                // :714-737
+    int selfRemovert(Session& s);                                              // :1378-1393 generalised to the configured schedule
+    int removeHighDynamicPoints();                                             // :1580-1604
+    int parseStaticScansViaProjection();                                       // :1534-1538
+    int detectLowDynamicPoints();                                              // :1413-1481
+    int filterStrongND(Session& target, Session& source);                      // :1403-1411
+    int filterStrongPD(Session& target, Session& source);                      // :1395-1401
+    int updateCurrentMap();                                                    // :1483-1524
+    int parseUpdatedStaticScansViaProjection();                                // :1551-1561
+    int parseLDScansViaProjection();                                           // :1564-1577
+    int updateScansScanwise();                                                 // :1540-1548 -> Session.cpp:362-380
+    int run_step0();
+    int run_step12();
+    int run_step3();
+
+    // ---- Session methods (Session.cpp) ----
+    int parseScansViaProjection(Session& s, ltr_cloud map, ltr_scanset* vec_to_store);     // Session.cpp:348-360
+    int extractLowDynPointsViaKnnDiff(Session& s, ltr_cloud target_map);                   // Session.cpp:393-427
+    int extractHighDynPointsViaKnnDiff(Session& s, ltr_cloud target_map);                  // Session.cpp:487-504
+    int constructGlobalNDMap(Session& s);                                                  // Session.cpp:430-435
+    int constructGlobalPDMap(Session& s);                                                  // Session.cpp:437-445
+    int removeWeakNDMapPointsHavingStrongNDInNear(Session& s);                             // Session.cpp:452-484
+    int mergeScansWithinGlobalCoordUtil(Session& s, ltr_scanset scans, ltr_cloud* out);    // utility.cpp:170-192 (+ rank gather)
+    int octreeDownsampling(ltr_cloud* cloud, float leaf);                                  // utility.cpp:204-219, in place
+
+    // ---- plumbing ----
+    int load_session(int sess, const float* xyzi, const int64_t* offsets, const double* poses, const double* inv_poses, int K);
+    int set(ltr_cloud* slot, ltr_cloud v);         // frees what the slot held, then stores v
+    int set(ltr_scanset* slot, ltr_scanset v, bool);
+    int assign(ltr_cloud* dst, ltr_cloud src);     // "*dst = *src" (deep copy)
+    int append(ltr_cloud* dst, ltr_cloud src);     // "*dst += *src"
+    int save(const std::string& name, ltr_cloud c);  // stands for pcl::io::savePCDFileBinary: keeps a device copy by name
+    int reduce_flags(ltr_cloud map);               // comm hook 1
+    int gather_cloud(ltr_cloud* cloud);            // comm hook 2+3: replaces a rank-local cloud by the rank-ordered concatenation
+    int fail(int code, const std::string& msg);
+
+    ltrh_params P;
+    ltr_ctx* ctx = nullptr;
+    ltr_comm comm{};
+    bool has_comm = false;
+    Session central_sess_, query_sess_;
+    std::map<std::string, ltr_cloud> saved;
+    std::map<std::string, double> timing;
+    std::vector<PassLog> log;
+    std::string err;
+
+private:
+    int partitionCurrentMapGeneric(ltr_cloud map, Session& source, ltr_scanset scans, int mode, float res, const char* what,
+                                   ltr_cloud* stat, ltr_cloud* dyn);
+};
+
+}  // namespace ltremovert_b200
