@@ -157,6 +157,15 @@ void ltr_reset_rimg_size(float vfov, float hfov, float alpha, int32_t* rows, int
 /* Statistics of the last ltr_remove_pass / ltr_parse_projected: [0] points projected, [1] taken by the fast path,
  * [2] sent to the exact path, [3] atomics issued, [4] kernel time in microseconds (CUDA events). */
 int ltr_last_pass_stats(ltr_ctx* ctx, double* stats5);
+/* Accumulated CUDA-event profile of the dominant kernels since the last reset:
+ * [0..3] map-projection kernel of ltr_remove_pass: total microseconds, launches, algorithmic bytes
+ *        (sum over launches of keyframes_in_launch * (12 N + N/8)), point-projections;
+ * [4..7] the same for the projection kernel of ltr_parse_projected (bytes: keyframes * 12 N). */
+int ltr_profile_get(ltr_ctx* ctx, double* out8);
+int ltr_profile_reset(ltr_ctx* ctx);
+/* CUDA-event stopwatch on the context's own stream (the stream every kernel of this library is launched on). */
+int ltr_timer_start(ltr_ctx* ctx);
+int ltr_timer_stop(ltr_ctx* ctx, double* milliseconds);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,9 @@ int ltrh_load_session(ltrh_removerter* r, int32_t sess, const float* xyzi, const
 int ltrh_run_step0(ltrh_removerter* r);   /* precleaningKeyframes(2.5) + makeGlobalMap            (:1660-1662) */
 int ltrh_run_step12(ltrh_removerter* r);  /* removeHighDynamicPoints + parseStaticScansViaProjection + detectLowDynamicPoints (:1665-1669) */
 int ltrh_run_step3(ltrh_removerter* r);   /* updateCurrentMap .. updateScansScanwise               (:1672-1675) */
+/* Benchmark/test plumbing (not in the reference): restores the state right after Step 0 (map_global_curr_ = the
+ * voxelised original map, everything derived freed) so that Step 1+2 can be timed repeatedly; clears log and timings. */
+int ltrh_reset_to_step0(ltrh_removerter* r);
 /* a single member function of Removerter by name, e.g. "removeHighDynamicPoints" */
 int ltrh_stage(ltrh_removerter* r, const char* name);
 

@@ -36,7 +36,7 @@ EXPORTS = [
     "ltr_scanset_free", "ltr_scanset_concat_per_keyframe", "ltr_scanset_flatten", "ltr_poses_upload", "ltr_poses_free",
     "ltr_preclean", "ltr_merge_scans_global", "ltr_voxel_centroid", "ltr_voxel_centroid_per_keyframe", "ltr_remove_pass",
     "ltr_flags_device_ptr", "ltr_flags_download", "ltr_flags_upload", "ltr_apply_partition", "ltr_parse_projected",
-    "ltr_knn_diff", "ltr_knn_split_cloud", "ltr_debug_pixel_index", "ltr_reset_rimg_size", "ltr_last_pass_stats",
+    "ltr_knn_diff", "ltr_knn_split_cloud", "ltr_debug_pixel_index", "ltr_reset_rimg_size", "ltr_last_pass_stats", "ltr_profile_get", "ltr_profile_reset", "ltr_timer_start", "ltr_timer_stop",
 ]
 
 
@@ -93,6 +93,10 @@ def lib():
     L.ltr_reset_rimg_size.argtypes = [f32, f32, f32, P(i32), P(i32)]
     L.ltr_reset_rimg_size.restype = None
     L.ltr_last_pass_stats.argtypes = [vp, vp]
+    L.ltr_profile_get.argtypes = [vp, vp]
+    L.ltr_profile_reset.argtypes = [vp]
+    L.ltr_timer_start.argtypes = [vp]
+    L.ltr_timer_stop.argtypes = [vp, P(ctypes.c_double)]
     _LIB = L
     return L
 
@@ -305,6 +309,22 @@ class Context:
         s = np.zeros(5, np.float64)
         self._ck(lib().ltr_last_pass_stats(self._h, s.ctypes.data))
         return s
+
+    def profile_get(self):
+        s = np.zeros(8, np.float64)
+        self._ck(lib().ltr_profile_get(self._h, s.ctypes.data))
+        return s
+
+    def profile_reset(self):
+        self._ck(lib().ltr_profile_reset(self._h))
+
+    def timer_start(self):
+        self._ck(lib().ltr_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_double()
+        self._ck(lib().ltr_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
 
     def kernel_launches(self):
         return lib().ltr_kernel_launches(self._h)

@@ -492,6 +492,30 @@ int Removerter::run_step3() {
     return LTR_OK;
 }
 
+int Removerter::reset_to_step0() {
+    for (Session* s : {&central_sess_, &query_sess_}) {
+        auto it = saved.find("OriginalNoisy" + s->sess_type_ + "MapGlobal");
+        if (it == saved.end()) return fail(LTR_ERR_INVALID, "reset_to_step0: Step 0 has not run");
+        for (auto& kv : s->cloud_names()) {
+            if (kv.first == "map_global_orig_" || kv.first == "map_global_curr_") continue;
+            if (*kv.second >= 0) { CK(ltr_cloud_free(ctx, *kv.second)); *kv.second = -1; }
+        }
+        for (auto& kv : s->scanset_names()) {
+            if (kv.first == "keyframe_scans_") continue;
+            if (*kv.second >= 0) { CK(ltr_scanset_free(ctx, *kv.second)); *kv.second = -1; }
+        }
+        CK(assign(&s->map_global_curr_, it->second));
+    }
+    for (auto it = saved.begin(); it != saved.end();) {
+        if (it->first.rfind("OriginalNoisy", 0) == 0) { ++it; continue; }
+        CK(ltr_cloud_free(ctx, it->second));
+        it = saved.erase(it);
+    }
+    log.clear();
+    timing.clear();
+    return LTR_OK;
+}
+
 }  // namespace ltremovert_b200
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -552,6 +576,7 @@ int ltrh_load_session(ltrh_removerter* r, int32_t sess, const float* xyzi, const
 int ltrh_run_step0(ltrh_removerter* r) { r->R->err.clear(); return r->R->run_step0(); }
 int ltrh_run_step12(ltrh_removerter* r) { r->R->err.clear(); return r->R->run_step12(); }
 int ltrh_run_step3(ltrh_removerter* r) { r->R->err.clear(); return r->R->run_step3(); }
+int ltrh_reset_to_step0(ltrh_removerter* r) { r->R->err.clear(); return r->R->reset_to_step0(); }
 
 int ltrh_stage(ltrh_removerter* r, const char* name) {
     Removerter& R = *r->R;

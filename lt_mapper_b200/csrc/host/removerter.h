@@ -65,6 +65,7 @@ public:
     int run_step0();
     int run_step12();
     int run_step3();
+    int reset_to_step0();  // benchmark plumbing, see include/ltr_removert.h
 
     // ---- Session methods (Session.cpp) ----
     int parseScansViaProjection(Session& s, ltr_cloud map, ltr_scanset* vec_to_store);     // Session.cpp:348-360

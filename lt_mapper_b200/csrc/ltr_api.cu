@@ -180,6 +180,10 @@ int ltr_create(ltr_ctx** out, const ltr_config* cfg) {
         delete ctx;
         return fail(nullptr, LTR_ERR_CUDA, "stream/event creation failed");
     }
+    cudaEventCreate(&ctx->ev_timer0);
+    cudaEventCreate(&ctx->ev_timer1);
+    ctx->ev_pool.resize(512);
+    for (auto& e2 : ctx->ev_pool) cudaEventCreate(&e2);
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
@@ -208,6 +212,9 @@ void ltr_destroy(ltr_ctx* ctx) {
     dev_free(ctx, ctx->d_ext);
     dev_free(ctx, ctx->d_counters);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& e2 : ctx->ev_pool) cudaEventDestroy(e2);
+    cudaEventDestroy(ctx->ev_timer0);
+    cudaEventDestroy(ctx->ev_timer1);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -377,6 +384,32 @@ void ltr_reset_rimg_size(float vfov, float hfov, float alpha, int32_t* rows, int
     // resetRimgSize (utility.cpp:222-236): int = std::round(float * float)
     *rows = (int32_t)roundf(vfov * alpha);
     *cols = (int32_t)roundf(hfov * alpha);
+}
+
+int ltr_profile_get(ltr_ctx* ctx, double* out8) {
+    if (!ctx || !out8) return LTR_ERR_INVALID;
+    for (int i = 0; i < 8; ++i) out8[i] = ctx->prof[i];
+    return LTR_OK;
+}
+int ltr_profile_reset(ltr_ctx* ctx) {
+    if (!ctx) return LTR_ERR_INVALID;
+    for (int i = 0; i < 8; ++i) ctx->prof[i] = 0.0;
+    return LTR_OK;
+}
+
+int ltr_timer_start(ltr_ctx* ctx) {
+    if (!ctx) return LTR_ERR_INVALID;
+    LTR_CUDA(ctx, cudaEventRecord(ctx->ev_timer0, ctx->stream));
+    return LTR_OK;
+}
+int ltr_timer_stop(ltr_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return LTR_ERR_INVALID;
+    LTR_CUDA(ctx, cudaEventRecord(ctx->ev_timer1, ctx->stream));
+    LTR_CUDA(ctx, cudaEventSynchronize(ctx->ev_timer1));
+    float f = 0.0f;
+    LTR_CUDA(ctx, cudaEventElapsedTime(&f, ctx->ev_timer0, ctx->ev_timer1));
+    *ms = (double)f;
+    return LTR_OK;
 }
 
 int ltr_last_pass_stats(ltr_ctx* ctx, double* s) {

@@ -45,7 +45,7 @@ struct ltr_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_timer0 = nullptr, ev_timer1 = nullptr;
     std::string err;
     std::vector<ltr::DevCloud> clouds;
     std::vector<ltr::DevScanSet> scansets;
@@ -55,6 +55,11 @@ struct ltr_ctx {
     double* d_ext = nullptr;      // 24 doubles: base2lidar rows 0..2, lidar2base rows 0..2
     double stats[5] = {0, 0, 0, 0, 0};
     unsigned long long* d_counters = nullptr;  // 4 device counters for pass statistics
+    // per-kernel profile of the dominant kernel (map projection): CUDA-event time, launches, algorithmic bytes
+    std::vector<cudaEvent_t> ev_pool;          // pairs
+    int ev_used = 0;
+    double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // [0] remove-pass map kernel us, [1] launches, [2] algorithmic bytes, [3] point-projections
+                                               // [4] parse map kernel us, [5] launches, [6] algorithmic bytes, [7] point-projections
 };
 
 namespace ltr {

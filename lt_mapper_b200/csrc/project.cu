@@ -162,6 +162,22 @@ __global__ void debug_pixel_kernel(const float* __restrict__ xyz, int64_t n, Img
     row[i] = r; col[i] = c; range[i] = s.r; az[i] = s.az; el[i] = s.el;
 }
 
+// records an event pair around the dominant kernel; collected by prof_collect after the pass's final synchronisation
+static inline void prof_begin(ltr_ctx* ctx) { if (ctx->ev_used + 2 <= (int)ctx->ev_pool.size()) cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream); }
+static inline void prof_end(ltr_ctx* ctx) { if (ctx->ev_used + 2 <= (int)ctx->ev_pool.size()) { cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream); ctx->ev_used += 2; } }
+static inline void prof_collect(ltr_ctx* ctx, int slot, double bytes_per_launch_unit, double proj_per_launch_unit, const std::vector<int>& units) {
+    // units[i] = keyframes in launch i (only the launches that got an event pair are accumulated)
+    for (int i = 0; i * 2 + 1 < ctx->ev_used && i < (int)units.size(); ++i) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[2 * i], ctx->ev_pool[2 * i + 1]) != cudaSuccess) continue;
+        ctx->prof[slot + 0] += (double)ms * 1000.0;
+        ctx->prof[slot + 1] += 1.0;
+        ctx->prof[slot + 2] += bytes_per_launch_unit * units[i];
+        ctx->prof[slot + 3] += proj_per_launch_unit * units[i];
+    }
+    ctx->ev_used = 0;
+}
+
 static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, max_blocks));
 }
@@ -195,6 +211,8 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     const int B = std::max(1, std::min(ctx->cfg.keyframe_batch, kf_end - kf_begin));
     const bool cand = (mode != LTR_MODE_ND);
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    std::vector<int> launch_units;
+    ctx->ev_used = 0;
     if (map->n > 0 && kf_end > kf_begin) {
         void *p_rimg, *p_win;
         LTR_TRY(dev_alloc(ctx, &p_rimg, (size_t)B * npx * sizeof(uint32_t)));
@@ -215,10 +233,13 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
             }
             const unsigned mb = (unsigned)((map->n + 255) / 256);
             const size_t smem = (size_t)nb * 12 * sizeof(double);
+            prof_begin(ctx);
+            launch_units.push_back(nb);
             if (cand) map_project_kernel<true><<<mb, 256, smem, ctx->stream>>>(view(*map), poses->d, k0, nb, ctx->d_ext, ctx->ext_identity ? 1 : 0,
                                                                              ctx->cfg.transform_order, g, rimg, diff_thres, win);
             else map_project_kernel<false><<<mb, 256, smem, ctx->stream>>>(view(*map), poses->d, k0, nb, ctx->d_ext, ctx->ext_identity ? 1 : 0,
                                                                           ctx->cfg.transform_order, g, rimg, diff_thres, win);
+            prof_end(ctx);
             LTR_LAUNCH_CHECK(ctx);
             const unsigned rb = (unsigned)((nb * npx + 255) / 256);
             if (cand) resolve_kernel<true><<<rb, 256, 0, ctx->stream>>>(rimg, win, nb * npx, diff_thres, map->flags);
@@ -233,6 +254,7 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     LTR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    prof_collect(ctx, 0, 12.0 * (double)map->n + (double)map->n / 8.0, (double)map->n, launch_units);
     ctx->stats[0] = (double)map->n * (kf_end - kf_begin);
     ctx->stats[1] = 0; ctx->stats[2] = ctx->stats[0]; ctx->stats[3] = 0;
     ctx->stats[4] = (double)ms * 1000.0;
@@ -258,6 +280,8 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
     std::vector<int64_t> off((size_t)K + 1, 0);
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     void *p_list = nullptr, *p_cnt = nullptr;
+    std::vector<int> launch_units;
+    ctx->ev_used = 0;
     if (K > 0 && mapc.n > 0) {
         const int B = std::max(1, std::min(ctx->cfg.keyframe_batch, K));
         void* p_win;
@@ -270,8 +294,11 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
         for (int k0 = 0; k0 < K; k0 += B) {
             const int nb = std::min(B, K - k0);
             const unsigned mb = (unsigned)((mapc.n + 255) / 256);
+            prof_begin(ctx);
+            launch_units.push_back(nb);
             map_project_kernel<false><<<mb, 256, (size_t)nb * 12 * sizeof(double), ctx->stream>>>(view(mapc), posc.d, kf_begin + k0, nb, ctx->d_ext,
                 ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, nullptr, 0.0f, win);
+            prof_end(ctx);
             LTR_LAUNCH_CHECK(ctx);
             parse_compact_kernel<<<nb, 1024, 0, ctx->stream>>>(win, (int)npx, (uint32_t*)p_list + (size_t)k0 * npx, (unsigned int*)p_cnt + k0);
             LTR_LAUNCH_CHECK(ctx);
@@ -295,6 +322,7 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
     LTR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    prof_collect(ctx, 4, 12.0 * (double)mapc.n, (double)mapc.n, launch_units);
     ctx->stats[0] = (double)mapc.n * K;
     ctx->stats[1] = 0; ctx->stats[2] = ctx->stats[0]; ctx->stats[3] = 0;
     ctx->stats[4] = (double)ms * 1000.0;

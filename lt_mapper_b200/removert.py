@@ -41,7 +41,7 @@ class Comm(ctypes.Structure):
 
 
 HOST_EXPORTS = ["ltrh_params_default", "ltrh_create", "ltrh_destroy", "ltrh_last_error", "ltrh_set_comm", "ltrh_context",
-                "ltrh_load_session", "ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_stage", "ltrh_cloud",
+                "ltrh_load_session", "ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0", "ltrh_stage", "ltrh_cloud",
                 "ltrh_scanset", "ltrh_timing", "ltrh_log_count", "ltrh_log_get"]
 
 
@@ -66,7 +66,7 @@ def host_lib():
     L.ltrh_context.argtypes = [vp]
     L.ltrh_context.restype = vp
     L.ltrh_load_session.argtypes = [vp, i32, vp, vp, vp, vp, i32]
-    for f in ("ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3"):
+    for f in ("ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0"):
         getattr(L, f).argtypes = [vp]
     L.ltrh_stage.argtypes = [vp, ctypes.c_char_p]
     L.ltrh_cloud.argtypes = [vp, ctypes.c_char_p, i32, P(i32)]
@@ -100,13 +100,22 @@ class TorchDistComm:
         self.struct = Comm(self.rank, self.world, None, *self._cb)
 
     def _tensor(self, ptr, n, typestr, dtype):
-        return self.torch.as_tensor(_DevArray(ptr, n, typestr), device=self.device)
+        if self.device.type == "cuda":
+            return self.torch.as_tensor(_DevArray(ptr, n, typestr), device=self.device)
+        # host memory (gloo tests of the hook logic): alias the buffer through numpy
+        ct = ctypes.c_uint8 if typestr == "|u1" else ctypes.c_float
+        arr = np.ctypeslib.as_array(ctypes.cast(ctypes.c_void_p(ptr), ctypes.POINTER(ct)), shape=(int(n),))
+        return self.torch.from_numpy(arr)
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            self.torch.cuda.synchronize()
 
     def _allreduce(self, user, dev, n):
         try:
             t = self._tensor(dev, n, "|u1", self.torch.uint8)
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
-            self.torch.cuda.synchronize()
+            self._sync()
             return 0
         except Exception as e:  # noqa: BLE001 -- must not propagate through the C frame
             print("allreduce hook failed:", e)
@@ -136,13 +145,16 @@ class TorchDistComm:
             if n_local > 0:
                 send[:n_local] = self._tensor(src, n_local, "<f4", torch.float32)
             recv = torch.empty(mx * self.world, dtype=torch.float32, device=self.device)
-            self.dist.all_gather_into_tensor(recv, send, group=self.group)
+            if self.backend == "gloo":
+                self.dist.all_gather(list(recv.view(self.world, mx).unbind(0)), send, group=self.group)
+            else:
+                self.dist.all_gather_into_tensor(recv, send, group=self.group)
             out = self._tensor(dst, total, "<f4", torch.float32)
             for r in range(self.world):
                 if cnt[r]:
                     d = int(displs[r])
                     out[d:d + cnt[r]] = recv[r * mx:r * mx + cnt[r]]
-            torch.cuda.synchronize()
+            self._sync()
             return 0
         except Exception as e:  # noqa: BLE001
             print("allgatherv hook failed:", e)
@@ -226,6 +238,9 @@ class Removerter:
 
     def run_step3(self):
         self._ck(host_lib().ltrh_run_step3(self._h))
+
+    def reset_to_step0(self):
+        self._ck(host_lib().ltrh_reset_to_step0(self._h))
 
     def stage(self, name):
         self._ck(host_lib().ltrh_stage(self._h, name.encode()))

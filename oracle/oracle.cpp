@@ -83,7 +83,7 @@ void map2RangeImg(const Cloud& scan, const Params& p, int rows, int cols, std::v
     ptidx.assign((size_t)rows * cols, 0);  // utility.cpp:104: index image initialised to 0
     const int n = (int)scan.size();
     if (p.faithful) {
-#pragma omp parallel for num_threads(16)  // utility.cpp:109 hard-codes 16
+#pragma omp parallel for num_threads(p.omp_cores < 16 ? p.omp_cores : 16)  // utility.cpp:109 hard-codes 16
         for (int i = 0; i < n; ++i) {
             const Pt& q = scan[i];
             const Sph s = cart2sph(q.x, q.y, q.z);

@@ -23,7 +23,7 @@ def _lib():
             subprocess.check_call(["make", "-C", _HERE, "-s"])
         _LIB = ctypes.CDLL(path)
         _LIB.ltr_synth_session.restype = ctypes.c_int64
-        _LIB.ltr_synth_session.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        _LIB.ltr_synth_session.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     return _LIB
@@ -54,14 +54,15 @@ class SessionData:
 
 
 def make_session(session, K, seed=SEED, beams=64, az_steps=1800, max_range=100.0, noise=0.02, spacing=1.0,
-                 n_cars=200, n_poles=40, n_movers=10, threads=None):
+                 n_cars=200, n_poles=40, n_movers=10, threads=None, k0=0):
+    """Keyframes k0 .. k0+K-1 of `session` (0 = central, 1 = query)."""
     lib = _lib()
     threads = threads or os.cpu_count() or 1
     cap = K * beams * az_steps
     xyzi = np.empty((cap, 4), dtype=np.float32)
     offsets = np.zeros(K + 1, dtype=np.int64)
     poses = np.zeros((K, 4, 4), dtype=np.float64)
-    n = lib.ltr_synth_session(seed, session, K, beams, az_steps, max_range, noise, spacing, n_cars, n_poles, n_movers,
+    n = lib.ltr_synth_session(seed, session, k0, K, beams, az_steps, max_range, noise, spacing, n_cars, n_poles, n_movers,
                               threads, xyzi.ctypes.data, offsets.ctypes.data, poses.ctypes.data)
     return SessionData(xyzi[:n].copy() if n < cap else xyzi, offsets, poses)
 

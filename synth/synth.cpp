@@ -69,9 +69,7 @@ void buildStatic(const SynthCfg& c, std::vector<Box>& boxes) {
             if (occ > (double)c.n_cars / 312.0) continue;
             const double life = u01(mix64(h + 1));
             // 15 % only in session 0 (-> ND), 15 % only in session 1 (-> PD), 70 % in both
-            const bool in0 = life < 0.85, in1 = life >= 0.15 && (life < 0.70 + 0.15 || life >= 0.85);
             const bool only0 = life < 0.15, only1 = life >= 0.85;
-            (void)in0; (void)in1;
             if (c.session == 0 && only1) continue;
             if (c.session == 1 && only0) continue;
             const double y = -35 + 10 * row, x = -57 + 3 * slot;
@@ -160,15 +158,15 @@ inline bool rayBox(const Box& b, const double* o, const double* d, double tmax, 
 
 extern "C" {
 
-// poses_out: K*16 doubles.
-void ltr_synth_poses(uint64_t seed, int session, int K, double spacing, double* poses_out) {
+// poses_out: K*16 doubles for keyframes k0 .. k0+K-1.
+void ltr_synth_poses(uint64_t seed, int session, int k0, int K, double spacing, double* poses_out) {
     SynthCfg c{}; c.seed = seed; c.session = session; c.K = K; c.spacing = spacing;
-    for (int k = 0; k < K; ++k) poseOf(c, k, poses_out + 16 * (size_t)k);
+    for (int k = 0; k < K; ++k) poseOf(c, k0 + k, poses_out + 16 * (size_t)k);
 }
 
 // Generates K scans. xyzi_out must hold K*beams*az_steps*4 floats (upper bound); offsets_out K+1 int64.
 // Returns the total number of points written.
-int64_t ltr_synth_session(uint64_t seed, int session, int K, int beams, int az_steps, double max_range, double noise_sigma,
+int64_t ltr_synth_session(uint64_t seed, int session, int k0, int K, int beams, int az_steps, double max_range, double noise_sigma,
                           double spacing, int n_cars, int n_poles, int n_movers, int threads,
                           float* xyzi_out, int64_t* offsets_out, double* poses_out) {
     SynthCfg c{}; c.seed = seed; c.session = session; c.K = K; c.beams = beams; c.az_steps = az_steps; c.max_range = max_range;
@@ -180,10 +178,11 @@ int64_t ltr_synth_session(uint64_t seed, int session, int K, int beams, int az_s
     std::vector<float> tmp((size_t)K * per * 4);  // scratch, compacted afterwards
     const int nb = 720;                            // world-azimuth bins for box culling
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : 1)
-    for (int k = 0; k < K; ++k) {
+    for (int kk = 0; kk < K; ++kk) {
+        const int k = k0 + kk;  // absolute keyframe index along the trajectory
         double T[16];
         poseOf(c, k, T);
-        std::memcpy(poses_out + 16 * (size_t)k, T, sizeof(T));
+        std::memcpy(poses_out + 16 * (size_t)kk, T, sizeof(T));
         std::vector<Box> boxes = stat;
         moversAt(c, k, boxes);
         const double o[3] = {T[3], T[7], T[11]};
@@ -205,7 +204,7 @@ int64_t ltr_synth_session(uint64_t seed, int session, int K, int beams, int az_s
             const int q0 = (int)std::floor((aref + amin + kPi) / (2 * kPi) * nb) - 1, q1 = (int)std::floor((aref + amax + kPi) / (2 * kPi) * nb) + 1;
             for (int q = q0; q <= q1; ++q) bins[((q % nb) + nb) % nb].push_back(bi);
         }
-        float* out = tmp.data() + (size_t)k * per * 4;
+        float* out = tmp.data() + (size_t)kk * per * 4;
         int64_t cnt = 0;
         for (int a = 0; a < az_steps; ++a) {
             const double az = -kPi + 2 * kPi * (a + 0.5) / az_steps;
@@ -234,7 +233,7 @@ int64_t ltr_synth_session(uint64_t seed, int session, int K, int beams, int az_s
                 ++cnt;
             }
         }
-        counts[k] = cnt;
+        counts[kk] = cnt;
     }
     offsets_out[0] = 0;
     for (int k = 0; k < K; ++k) offsets_out[k + 1] = offsets_out[k] + counts[k];

@@ -1,0 +1,216 @@
+"""Known-answer tests that pin the oracle (the reference ships no tests: SURVEY.md section 4 / 8c).
+Each case is derived by hand from the cited reference lines."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+
+def test_reset_rimg_size():
+    # utility.cpp:222-236 with float32 semantics
+    exp = {2.5: (125, 900), 2.375: (119, 855), 2.0: (100, 720), 1.9: (95, 684), 1.5: (75, 540), 1.425: (71, 513), 3.0: (150, 1080), 1.0: (50, 360)}
+    for a, rc in exp.items():
+        assert oracle.reset_rimg_size(a) == rc
+
+
+def test_pixel_mapping_known_answers():
+    # utility.cpp:118-123 at 125x900: round-then-clamp makes col 899 absorb 900 and col 0 half width
+    pts = np.array([[10, 0, 0], [0, 10, 0], [-10, 0, 0], [-10, -1e-6, 0], [0, 0, 0], [0, -10, 0]], np.float32)
+    r, c, rg = oracle.pixel_index(pts, 125, 900)
+    assert list(r) == [63] * 6
+    assert list(c) == [450, 675, 899, 0, 450, 225]
+    assert list(rg) == [10, 10, 10, 10, 0, 10]
+    # elevation +-25 deg -> rows 0 / 124 (clamped from 125)
+    t = np.tan(np.deg2rad(25.0))
+    pts = np.array([[10, 0, 10 * t * 1.01], [10, 0, -10 * t * 1.01], [10, 0, 10 * t * 0.5]], np.float32)
+    r, _, _ = oracle.pixel_index(pts, 125, 900)
+    assert r[0] == 0 and r[1] == 124 and 0 < r[2] < 63
+
+
+def test_atan2f_equals_libm():
+    """ref_atan2f (fdlibm restatement) is bit-identical to this machine's glibc atan2f on the cart2sph call pattern."""
+    n = int(os.environ.get("LTR_ATAN_SAMPLES", "20000000"))
+    assert oracle.atan2f_selfcheck(12345, n) == 0
+    # special values
+    sp = np.array([0.0, -0.0, 1.0, -1.0, 1e-30, -1e-30, 1e30, -1e30, np.inf, -np.inf, 0.4375, 0.6875, 1.1875, 2.4375, 3e-10], np.float32)
+    y, x = np.meshgrid(sp, sp)
+    a = oracle.atan2f(y.ravel(), x.ravel())
+    b = oracle.atan2f(y.ravel(), x.ravel(), libm=True)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_winner_is_min_range_then_lowest_index():
+    # utility.cpp:134-138 sequential semantics: strict '<' -> first of equal ranges wins; index image initialised to 0
+    pts = np.array([[10, 0, 0, 1], [5, 0, 0, 2], [5, 0, 0, 3], [7, 0, 0, 4], [0, 20, 0, 5]], np.float32)
+    rimg, idx = oracle.map2rimg(pts, 125, 900)
+    assert rimg[63, 450] == 5.0 and idx[63, 450] == 1
+    assert rimg[63, 675] == 20.0 and idx[63, 675] == 4
+    assert rimg[0, 0] == 10000.0 and idx[0, 0] == 0
+    assert (rimg == 10000.0).sum() == 125 * 900 - 2
+    s = oracle.scan2rimg(pts, 125, 900)
+    assert np.array_equal(s, rimg)
+
+
+def _one_kf_pass(map_pts, scan_pts, mode, thres=0.1):
+    I = np.eye(4)
+    return oracle.remove_pass(np.asarray(map_pts, np.float32), np.asarray(scan_pts, np.float32), [0, len(scan_pts)], I[None], mode, 2.5, thres)
+
+
+def test_dynamic_threshold_is_strict_and_signed():
+    # Removerter.cpp:401-402: dynamic <=> thres < diff < 200, diff = scan - map (HD/PD) or map - scan (ND)
+    scan = [[10, 0, 0, 0]]
+    f = lambda r: [float(np.float32(r)), 0, 0, 0]  # noqa: E731
+    near = float(np.float32(10) - np.float32(0.1))  # scan - map == fl(0.1)-ish boundary
+    m = [f(9.0), [0, 50, 0, 0], [0, -60, 0, 0]]
+    assert list(_one_kf_pass(m, scan, oracle.MODE_HD)) == [1, 0, 0]          # 10 - 9 = 1 > 0.1 ; other pixels: scan empty -> diff ~ 9950 > 200
+    assert list(_one_kf_pass(m, scan, oracle.MODE_ND)) == [0, 0, 0]          # 9 - 10 < 0
+    m2 = [f(10.5), [0, 50, 0, 0], [0, -60, 0, 0]]
+    assert list(_one_kf_pass(m2, scan, oracle.MODE_ND)) == [1, 0, 0]         # map - scan = 0.5
+    assert list(_one_kf_pass(m2, scan, oracle.MODE_PD)) == [0, 0, 0]
+    # exact threshold: diff == thres is NOT dynamic (strict '>')
+    d = np.float32(10) - np.float32(near)
+    assert list(_one_kf_pass([f(near), [0, 50, 0, 0], [0, -60, 0, 0]], scan, oracle.MODE_HD, thres=float(d))) == [0, 0, 0]
+    assert list(_one_kf_pass([f(near), [0, 50, 0, 0], [0, -60, 0, 0]], scan, oracle.MODE_HD, thres=float(np.nextafter(d, np.float32(0))))) == [1, 0, 0]
+    # only the pixel winner can be flagged, even if a farther point in the same pixel also passes the threshold
+    m3 = [f(5.0), f(6.0), f(7.0)]
+    assert list(_one_kf_pass(m3, scan, oracle.MODE_HD)) == [1, 0, 0]
+    # upper bound: diff >= 200 is not dynamic (kValidDiffUpperBound)
+    assert list(_one_kf_pass([f(1.0), [0, 50, 0, 0], [0, -60, 0, 0]], [[250, 0, 0, 0]], oracle.MODE_HD)) == [0, 0, 0]
+    # map point index 0 CAN be flagged by the remove test (unlike parseProjectedPoints)
+    assert _one_kf_pass(m, scan, oracle.MODE_HD)[0] == 1
+
+
+def test_parse_projected_skips_index_zero():
+    # utility.cpp:82: ptidx == 0 means "no point" -> map point 0 is never emitted even when visible
+    m = np.array([[10, 0, 0, 7], [0, 10, 0, 8], [0, 20, 0, 9], [-5, 0, 1, 10]], np.float32)
+    pts, idx = oracle.parse_projected(m, np.eye(4), 3.0)
+    assert list(idx) == sorted(idx, key=lambda i: 0) and set(idx) == {1, 3}   # point 0 dropped, point 2 occluded by 1
+    r, c, _ = oracle.pixel_index(m[idx, :3], 150, 1080)
+    assert list(r * 1080 + c) == sorted(r * 1080 + c)                          # row-major pixel order
+    assert np.array_equal(pts, m[idx])
+
+
+def test_transform_orders_and_two_step_rounding():
+    rng = np.random.default_rng(0)
+    T = np.eye(4); T[:3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]; T[:3, 3] = [123.456, -78.9, 1.9]
+    p = rng.uniform(-100, 100, (200000, 4)).astype(np.float32)
+    for order in (0, 1):
+        o = oracle.transform(p, T, order)
+        x, y, z = (p[:, i].astype(np.float64) for i in range(3))
+        if order == 0:
+            e = [((T[r, 0] * x + T[r, 1] * y) + T[r, 2] * z) + T[r, 3] for r in range(3)]
+        else:
+            e = [((T[r, 3] + x * T[r, 0]) + y * T[r, 1]) + z * T[r, 2] for r in range(3)]
+        assert np.array_equal(o[:, :3], np.stack(e, 1).astype(np.float32))
+        assert np.array_equal(o[:, 3], p[:, 3])
+    # identity is exact
+    assert np.array_equal(oracle.transform(p, np.eye(4)), p)
+    # the two orders differ in rare last-bit cases only
+    d = oracle.transform(p, T, 0) != oracle.transform(p, T, 1)
+    assert d.mean() < 1e-3
+
+
+def test_inverse4x4():
+    rng = np.random.default_rng(1)
+    T = np.eye(4); T[:3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]; T[:3, 3] = [10, -20, 2]
+    assert np.allclose(oracle.inverse4x4(T) @ T, np.eye(4), atol=1e-13)
+
+
+def test_octree_voxel_known_answer():
+    """OctreePointCloudVoxelCentroid hand case (leaf 0.05): bounding box [0,0.06]x[0,0.02]x[0,0.06] (+pad) -> depth 1,
+    cube side 0.1 centred per axis; keys A=(0,0,0) B=(0,1,0) C=(0,0,1) D=(1,0,0); DFS child order (x<<2|y<<1|z):
+    A(0), C(1), B(2), D(4)."""
+    A, B, C, D = [0, 0, 0, 1], [0.02, 0.02, 0.02, 2], [0, 0, 0.06, 3], [0.06, 0, 0, 4]
+    out = oracle.voxel(np.array([A, B, C, D], np.float32), 0.05)
+    assert np.array_equal(out, np.array([A, C, B, D], np.float32))
+    # two points in one voxel -> f32 sums in insertion order / count, all four fields
+    P = np.array([[0.001, 0.002, 0.003, 10], [0.004, 0.001, 0.002, 20], [1.0, 1.0, 1.0, 5]], np.float32)
+    out = oracle.voxel(P, 0.05)
+    assert len(out) == 2
+    e = (P[0] + P[1]) / np.float32(2)
+    assert np.array_equal(out[0], e) and np.array_equal(out[1], P[2])
+    assert len(oracle.voxel(np.zeros((0, 4), np.float32), 0.05)) == 0
+
+
+def test_octree_voxel_properties():
+    rng = np.random.default_rng(3)
+    p = rng.uniform(-20, 20, (50000, 4)).astype(np.float32)
+    p[:, 2] *= 0.1
+    v = oracle.voxel(p, 0.4)
+    assert 0 < len(v) < len(p)
+    # re-voxelising shrinks or keeps the count (new bounding box => not idempotent in general)
+    assert len(oracle.voxel(v, 0.4)) <= len(v)
+    # every centroid lies inside the data's bounding box and the point mass is conserved within f32 error
+    assert (v[:, :3].min(0) >= p[:, :3].min(0)).all() and (v[:, :3].max(0) <= p[:, :3].max(0)).all()
+    # permutation of the input changes only which insertion order sums use: same voxel count
+    assert len(oracle.voxel(p[rng.permutation(len(p))], 0.4)) == len(v)
+
+
+def test_knn_uses_squared_distances_and_exact_search():
+    rng = np.random.default_rng(5)
+    t = rng.uniform(-5, 5, (4000, 4)).astype(np.float32)
+    q = rng.uniform(-6, 6, (500, 4)).astype(np.float32)
+    for k in (1, 2, 3, 5):
+        a = oracle.knn_dists(q, t, k)
+        b = oracle.knn_dists(q, t, k, brute=True)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # FLANN L2_Simple: ((dx*dx) + dy*dy) + dz*dz in f32
+    d = (q[:1, None, :3] - t[None, :, :3]).astype(np.float32)
+    e = ((d[..., 0] * d[..., 0]) + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    assert oracle.knn_dists(q[:1], t, 1)[0, 0] == np.sort(e[0])[0]
+    # decision: mean of k SQUARED distances < thr (Session.cpp:592-596); a point 0.15 m away is "coexist" for thr 0.04 (k=1)
+    tgt = np.array([[0, 0, 0, 0], [10, 10, 10, 0]], np.float32)
+    scan = np.array([[0.15, 0, 0, 0], [0.25, 0, 0, 0]], np.float32)
+    lab, co, di = oracle.knn_partition(scan, np.eye(4), np.eye(4), tgt, 1, 0.04)
+    assert list(lab) == [0, 1] and len(co) == 1 and len(di) == 1
+    # k = 2 divides by k even though the second neighbour is far: mean = (0.0225 + ~300)/2 -> diff
+    lab, _, _ = oracle.knn_partition(scan, np.eye(4), np.eye(4), tgt, 2, 0.04)
+    assert list(lab) == [1, 1]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/ltslam/include/ltslam/nanoflann.hpp"), reason="reference not mounted")
+def test_kdtree_against_reference_nanoflann(tmp_path):
+    """Cross-check of the oracle's exact kNN against the reference's vendored nanoflann 1.3.2 (included by path, never copied)."""
+    import subprocess
+    src = tmp_path / "nf.cpp"
+    src.write_text(r'''
+#include "/root/reference/ltslam/include/ltslam/nanoflann.hpp"
+#include <cstdio>
+#include <vector>
+struct PC { std::vector<float> p; size_t kdtree_get_point_count() const { return p.size()/3; }
+  float kdtree_get_pt(size_t i, size_t d) const { return p[3*i+d]; } template <class B> bool kdtree_get_bbox(B&) const { return false; } };
+int main(int argc, char** argv) { FILE* f = fopen(argv[1], "rb"); int nt, nq, k; fread(&nt,4,1,f); fread(&nq,4,1,f); fread(&k,4,1,f);
+  PC pc; pc.p.resize(3*nt); fread(pc.p.data(),4,3*nt,f); std::vector<float> q(3*nq); fread(q.data(),4,3*nq,f); fclose(f);
+  typedef nanoflann::KDTreeSingleIndexAdaptor<nanoflann::L2_Simple_Adaptor<float, PC>, PC, 3> T; T tree(3, pc, nanoflann::KDTreeSingleIndexAdaptorParams(15)); tree.buildIndex();
+  FILE* o = fopen(argv[2], "wb"); std::vector<size_t> idx(k); std::vector<float> d(k);
+  for (int i = 0; i < nq; ++i) { tree.knnSearch(&q[3*i], k, idx.data(), d.data()); fwrite(d.data(),4,k,o); } fclose(o); }
+''')
+    exe = tmp_path / "nf"
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-o", str(exe), str(src)])
+    rng = np.random.default_rng(11)
+    t = rng.uniform(-30, 30, (20000, 4)).astype(np.float32)
+    q = rng.uniform(-30, 30, (2000, 4)).astype(np.float32)
+    k = 3
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.array([len(t), len(q), k], np.int32).tobytes()); f.write(t[:, :3].tobytes()); f.write(q[:, :3].tobytes())
+    subprocess.check_call([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    ref = np.fromfile(tmp_path / "out.bin", np.float32).reshape(len(q), k)
+    assert np.array_equal(ref.view(np.uint32), oracle.knn_dists(q, t, k).view(np.uint32))
+
+
+def test_faithful_mode_matches_exact_mode_single_thread(small_pair):
+    """The reference-structured timing path (materialised transforms, std::set complement) computes the same result
+    when its racy OpenMP loops run on one thread."""
+    c, q = (s.subset(0, 3) for s in small_pair)
+    res = []
+    for faithful in (False, True):
+        R = oracle.Removerter(num_knn=2, knn_thr=0.01, faithful=faithful, omp_cores=1, threads=2)
+        for s, d in ((0, c), (1, q)):
+            R.load_session(s, d.xyzi, d.offsets, d.poses)
+        R.run()
+        res.append([R.cloud(n, s) for s in (0, 1) for n in ("map_global_curr_static_", "map_global_nd_strong_", "map_global_pd_weak_")] + [R.log()])
+    for a, b in zip(res[0][:-1], res[1][:-1]):
+        assert np.array_equal(a, b)
+    assert res[0][-1] == res[1][-1]
