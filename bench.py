@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 KF_PER_GPU = 200                                   # keyframes per session per GPU (configs[1])
 SCHEDULE = [(0, 2.5), (0, 2.0), (0, 1.5), (1, 1.0)]  # 3 remove + 1 revert resolutions
 NUM_KNN, KNN_THR = 1, 0.04                         # k = 1, r = 0.2 m  ->  r^2 on the squared distance (Session.cpp:592-596)
-CPU_SAMPLE_KF = 10                                 # keyframes per session of the bounded CPU sample (configs[0] size)
+CPU_SAMPLE_KF = 20                                 # keyframes per session of the bounded CPU sample (~10-20 s of CPU work per step)
 METRIC = "keyframes/sec (two-session removert+diff)"
 LD_OUTPUTS = ["nd_map", "pd_map", "strong_nd_map", "weak_nd_map", "strong_pd_map", "weak_pd_map", "union_map_queryside",
               "union_map_centralside"]
@@ -42,49 +42,57 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs (a background thread
+    calling nvmlDeviceGetClockInfo / nvmlDeviceGetCurrentClocksEventReasons; `nvidia-smi -lms` was measured to slow the
+    launch-heavy step by ~30 % through driver-lock contention, direct NVML calls do not)."""
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index, period_s=0.05):
+        self.gpu, self.period, self.rows, self.stop_flag, self.thread, self.err = gpu_index, period_s, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, rs))
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(self.period)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + str(self.err)]}
+        self.stop_flag = True
+        self.thread.join(timeout=5)
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        reasons = set()
+        for _, rs in self.rows:
+            for n, bit in names.items():
+                if rs & bit:
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm), "reasons": sorted(reasons),
+                "samples": len(sm), "source": "nvml"}
 
 
 def gen_block(rank, kf):
@@ -151,6 +159,7 @@ def main():
     ap.add_argument("--kf", type=int, default=KF_PER_GPU, help="keyframes per session per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast-path", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: measure the sampler's own overhead")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,7 +212,8 @@ def main():
     barrier()
     R.ctx.profile_reset()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not args.no_clock_sampler:
+        sampler.start()
     l0 = R.ctx.kernel_launches()
     stage_t = {}
     barrier()

@@ -152,17 +152,26 @@ int ltr_knn_split_cloud(ltr_ctx* ctx, ltr_cloud query, ltr_cloud target, int32_t
 /* Evaluates the device restatement of cart2sph + pixel index (utility.cpp:38-56, 118-123) for n points. */
 int ltr_debug_pixel_index(ltr_ctx* ctx, const float* xyz /* n*3 */, int64_t n, int32_t rows, int32_t cols,
                           int32_t* row, int32_t* col, float* range, float* az, float* el);
+/* Fast-path validation: for n map points and one inverse pose, writes per point 8 floats:
+ * fast pre-round column, fast pre-round row, fast range, r/rho | reference pre-round column, row, range, 0;
+ * margins4 (optional) = column margin a, column margin b (x r/rho), row margin, relative range margin. */
+int ltr_debug_fast_project(ltr_ctx* ctx, const float* xyz /* n*3 */, int64_t n, const double* inv_pose16, float res_alpha,
+                           float* out8 /* n*8 */, float* margins4);
 /* resetRimgSize (utility.cpp:222-236) */
 void ltr_reset_rimg_size(float vfov, float hfov, float alpha, int32_t* rows, int32_t* cols);
-/* Statistics of the last ltr_remove_pass / ltr_parse_projected: [0] points projected, [1] taken by the fast path,
- * [2] sent to the exact path, [3] atomics issued, [4] kernel time in microseconds (CUDA events). */
-int ltr_last_pass_stats(ltr_ctx* ctx, double* stats5);
+/* Statistics of the last ltr_remove_pass / ltr_parse_projected: [0] (point, keyframe) pairs projected, [1] pairs settled by
+ * the fast path alone, [2] pairs that needed exact arithmetic, [3] atomics on the winner image, [4] kernel time of the
+ * pass in microseconds (CUDA events), [5] pairs that went through the FULL reference arithmetic. */
+int ltr_last_pass_stats(ltr_ctx* ctx, double* stats6);
 /* Accumulated CUDA-event profile of the dominant kernels since the last reset:
  * [0..3] map-projection kernel of ltr_remove_pass: total microseconds, launches, algorithmic bytes
  *        (sum over launches of keyframes_in_launch * (12 N + N/8)), point-projections;
  * [4..7] the same for the projection kernel of ltr_parse_projected (bytes: keyframes * 12 N). */
 int ltr_profile_get(ltr_ctx* ctx, double* out8);
 int ltr_profile_reset(ltr_ctx* ctx);
+/* With LTR_TRACE=1 in the environment every hot entry point is timed on the host between two stream synchronisations;
+ * this prints the per-entry-point totals to stderr (and clears them if reset != 0). */
+int ltr_trace_dump(ltr_ctx* ctx, int reset);
 /* CUDA-event stopwatch on the context's own stream (the stream every kernel of this library is launched on). */
 int ltr_timer_start(ltr_ctx* ctx);
 int ltr_timer_stop(ltr_ctx* ctx, double* milliseconds);

@@ -36,7 +36,7 @@ EXPORTS = [
     "ltr_scanset_free", "ltr_scanset_concat_per_keyframe", "ltr_scanset_flatten", "ltr_poses_upload", "ltr_poses_free",
     "ltr_preclean", "ltr_merge_scans_global", "ltr_voxel_centroid", "ltr_voxel_centroid_per_keyframe", "ltr_remove_pass",
     "ltr_flags_device_ptr", "ltr_flags_download", "ltr_flags_upload", "ltr_apply_partition", "ltr_parse_projected",
-    "ltr_knn_diff", "ltr_knn_split_cloud", "ltr_debug_pixel_index", "ltr_reset_rimg_size", "ltr_last_pass_stats", "ltr_profile_get", "ltr_profile_reset", "ltr_timer_start", "ltr_timer_stop",
+    "ltr_knn_diff", "ltr_knn_split_cloud", "ltr_debug_pixel_index", "ltr_debug_fast_project", "ltr_reset_rimg_size", "ltr_last_pass_stats", "ltr_profile_get", "ltr_profile_reset", "ltr_timer_start", "ltr_timer_stop", "ltr_trace_dump",
 ]
 
 
@@ -90,12 +90,14 @@ def lib():
     L.ltr_knn_diff.argtypes = [vp, i32, i32, i32, i32, i32, f32, P(i32), P(i32)]
     L.ltr_knn_split_cloud.argtypes = [vp, i32, i32, i32, f32, P(i32), P(i32)]
     L.ltr_debug_pixel_index.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]
+    L.ltr_debug_fast_project.argtypes = [vp, vp, i64, vp, f32, vp, vp]
     L.ltr_reset_rimg_size.argtypes = [f32, f32, f32, P(i32), P(i32)]
     L.ltr_reset_rimg_size.restype = None
     L.ltr_last_pass_stats.argtypes = [vp, vp]
     L.ltr_profile_get.argtypes = [vp, vp]
     L.ltr_profile_reset.argtypes = [vp]
     L.ltr_timer_start.argtypes = [vp]
+    L.ltr_trace_dump.argtypes = [vp, i32]
     L.ltr_timer_stop.argtypes = [vp, P(ctypes.c_double)]
     _LIB = L
     return L
@@ -305,8 +307,16 @@ class Context:
                                              rng.ctypes.data, az.ctypes.data, el.ctypes.data))
         return row, col, rng, az, el
 
+    def debug_fast_project(self, xyz, inv_pose, res_alpha):
+        x = _f32(xyz).reshape(-1, 3)
+        ip = np.ascontiguousarray(inv_pose, np.float64).reshape(16)
+        out = np.empty((len(x), 8), np.float32)
+        mg = np.zeros(4, np.float32)
+        self._ck(lib().ltr_debug_fast_project(self._h, x.ctypes.data, len(x), ip.ctypes.data, res_alpha, out.ctypes.data, mg.ctypes.data))
+        return out, mg
+
     def last_pass_stats(self):
-        s = np.zeros(5, np.float64)
+        s = np.zeros(6, np.float64)
         self._ck(lib().ltr_last_pass_stats(self._h, s.ctypes.data))
         return s
 
@@ -317,6 +327,9 @@ class Context:
 
     def profile_reset(self):
         self._ck(lib().ltr_profile_reset(self._h))
+
+    def trace_dump(self, reset=True):
+        self._ck(lib().ltr_trace_dump(self._h, 1 if reset else 0))
 
     def timer_start(self):
         self._ck(lib().ltr_timer_start(self._h))

@@ -67,22 +67,31 @@ __device__ __forceinline__ uint8_t knn_label(const Grid& g, const uint32_t* __re
     cell_of(g, qx, qy, qz, &cx, &cy, &cz);
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
     if (x0 <= x1) {
-        for (int dz = -1; dz <= 1; ++dz) {
-            const int z = cz + dz;
-            if (z < 0 || z >= g.dim[2]) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int y = cy + dy;
-                if (y < 0 || y >= g.dim[1]) continue;
-                const size_t row = ((size_t)z * g.dim[1] + y) * g.dim[0];
-                const uint32_t s = cell_start[row + x0], e = cell_start[row + x1 + 1];
-                for (uint32_t p = s; p < e; ++p) {
-                    const float4 t = sorted[p];
-                    const float d = l2_simple(qx, qy, qz, t.x, t.y, t.z);
-                    if (d < best[KT - 1]) {
-                        best[KT - 1] = d;
+        // rows of 3 x-adjacent cells, the query's own row first: most points have their k neighbours right there and
+        // leave through the early exit below
+        // (dy, dz) + 1 packed 2 bits per step: dy = {0,-1,1,0,0,-1,1,-1,1}, dz = {0,0,0,-1,1,-1,-1,1,1}
+        const unsigned pack_dy = 0x22161U, pack_dz = 0x28215U;
+#pragma unroll 1
+        for (int o = 0; o < 9; ++o) {
+            const int z = cz + (int)((pack_dz >> (2 * o)) & 3u) - 1, y = cy + (int)((pack_dy >> (2 * o)) & 3u) - 1;
+            if (z < 0 || z >= g.dim[2] || y < 0 || y >= g.dim[1]) continue;
+            const size_t row = ((size_t)z * g.dim[1] + y) * g.dim[0];
+            const uint32_t s = cell_start[row + x0], e = cell_start[row + x1 + 1];
+            for (uint32_t p = s; p < e; ++p) {
+                const float4 t = sorted[p];
+                const float d = l2_simple(qx, qy, qz, t.x, t.y, t.z);
+                if (d < best[KT - 1]) {
+                    best[KT - 1] = d;
 #pragma unroll
-                        for (int j = KT - 1; j > 0; --j)
-                            if (best[j] < best[j - 1]) { const float t2 = best[j]; best[j] = best[j - 1]; best[j - 1] = t2; }
+                    for (int j = KT - 1; j > 0; --j)
+                        if (best[j] < best[j - 1]) { const float t2 = best[j]; best[j] = best[j - 1]; best[j - 1] = t2; }
+                    // Early exit: the final k smallest distances are element-wise <= the current ones, and double sum, float
+                    // rounding and division are monotone, so "current mean < thr" already decides "near".
+                    if (KT <= 4 && best[k - 1 < KT ? k - 1 : KT - 1] != kInf) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int j = 0; j < KT; ++j) if (j < k) sum = da(sum, (double)best[j]);
+                        if (fabsf(fd(__double2float_rn(sum), (float)k)) < thr) return 0;
                     }
                 }
             }
@@ -205,6 +214,7 @@ extern "C" {
 
 int ltr_knn_diff(ltr_ctx* ctx, ltr_scanset scans_h, ltr_poses poses_h, int32_t pose_offset, ltr_cloud target_h, int32_t k, float thr,
                  ltr_scanset* out_coexist, ltr_scanset* out_diff) {
+    ApiTrace tr__(ctx, "ltr_knn_diff");
     if (!ctx) return LTR_ERR_INVALID;
     DevScanSet* sp;
     DevPoses* pp;
@@ -258,6 +268,7 @@ int ltr_knn_diff(ltr_ctx* ctx, ltr_scanset scans_h, ltr_poses poses_h, int32_t p
 }
 
 int ltr_knn_split_cloud(ltr_ctx* ctx, ltr_cloud query_h, ltr_cloud target_h, int32_t k, float thr, ltr_cloud* out_near, ltr_cloud* out_far) {
+    ApiTrace tr__(ctx, "ltr_knn_split_cloud");
     if (!ctx || !out_near || !out_far) return fail(ctx, LTR_ERR_INVALID, "null argument");
     DevCloud *qp, *tp;
     LTR_TRY(cloud_get(ctx, query_h, &qp));

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 
 thread_local std::string ltr::g_create_err;
 
@@ -132,6 +133,37 @@ static int download_points(ltr_ctx* ctx, const DevCloud& c, float* xyzi) {
     return LTR_OK;
 }
 
+// KfFast of one keyframe: M = base2lidar * inv_pose (3x4, double); q = A (p - c) = A (p - c_hi) - A c_lo, c = -A^-1 t, c_hi = fl32(c)
+static void make_kf_fast(const double* inv_pose /*12*/, const double* b2l /*16*/, bool ext_identity, float* out /*16*/) {
+    double M[12];
+    if (ext_identity) { for (int i = 0; i < 12; ++i) M[i] = inv_pose[i]; }
+    else {
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 4; ++c) {
+                double v = 0.0;
+                for (int j = 0; j < 3; ++j) v += b2l[r * 4 + j] * inv_pose[j * 4 + c];
+                if (c == 3) v += b2l[r * 4 + 3];
+                M[r * 4 + c] = v;
+            }
+    }
+    const double a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[6], g = M[8], h = M[9], i = M[10];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    bool ok = std::isfinite(det) && std::fabs(det) > 1e-6 && std::fabs(det) < 1e6;
+    double inv[9] = {(e * i - f * h), (c * h - b * i), (b * f - c * e), (f * g - d * i), (a * i - c * g), (c * d - a * f), (d * h - e * g), (b * g - a * h), (a * e - b * d)};
+    double cc[3] = {0, 0, 0};
+    if (ok) for (int r = 0; r < 3; ++r) cc[r] = -(inv[r * 3 + 0] * M[3] + inv[r * 3 + 1] * M[7] + inv[r * 3 + 2] * M[11]) / det;
+    for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) { out[r * 3 + k] = (float)M[r * 4 + k]; if (!std::isfinite(out[r * 3 + k])) ok = false; }
+    double clo[3];
+    for (int r = 0; r < 3; ++r) {
+        const float hi = (float)cc[r];
+        out[9 + r] = hi;                       // c_hi
+        clo[r] = cc[r] - (double)hi;
+        if (!std::isfinite(hi)) ok = false;
+    }
+    for (int r = 0; r < 3; ++r) out[12 + r] = (float)(M[r * 4 + 0] * clo[0] + M[r * 4 + 1] * clo[1] + M[r * 4 + 2] * clo[2]);  // t_lo = A c_lo
+    out[15] = ok ? 1.0f : 0.0f;
+}
+
 static bool is_identity(const double* m) {
     for (int i = 0; i < 16; ++i) if (m[i] != ((i % 5 == 0) ? 1.0 : 0.0)) return false;
     return true;
@@ -175,6 +207,7 @@ int ltr_create(ltr_ctx** out, const ltr_config* cfg) {
     ctx->device = cfg->device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->ext_identity = is_identity(cfg->lidar2base) && is_identity(cfg->base2lidar);
+    { const char* t = getenv("LTR_TRACE"); ctx->trace = t && t[0] == '1'; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         delete ctx;
@@ -206,9 +239,10 @@ int ltr_create(ltr_ctx** out, const ltr_config* cfg) {
 void ltr_destroy(ltr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->trace) ltr_trace_dump(ctx, 1);
     for (auto& c : ctx->clouds) if (c.used) cloud_release(ctx, &c);
     for (auto& s : ctx->scansets) if (s.used) { cloud_release(ctx, &s.pts); dev_free(ctx, s.d_off); }
-    for (auto& p : ctx->poses) if (p.used) dev_free(ctx, p.d);
+    for (auto& p : ctx->poses) if (p.used) { dev_free(ctx, p.d); dev_free(ctx, p.d_fast); }
     dev_free(ctx, ctx->d_ext);
     dev_free(ctx, ctx->d_counters);
     cudaStreamSynchronize(ctx->stream);
@@ -232,6 +266,7 @@ int ltr_synchronize(ltr_ctx* ctx) {
 int64_t ltr_kernel_launches(const ltr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int ltr_cloud_upload(ltr_ctx* ctx, const float* xyzi, int64_t n, ltr_cloud* out) {
+    ApiTrace tr__(ctx, "ltr_cloud_upload");
     if (!ctx || !out || (n > 0 && !xyzi)) return fail(ctx, LTR_ERR_INVALID, "null argument");
     LTR_TRY(cloud_new(ctx, n, out));
     return upload_points(ctx, xyzi, ctx->clouds[*out]);
@@ -247,6 +282,7 @@ int ltr_cloud_size(ltr_ctx* ctx, ltr_cloud c, int64_t* n) {
     return LTR_OK;
 }
 int ltr_cloud_download(ltr_ctx* ctx, ltr_cloud c, float* xyzi, int64_t capacity, int64_t* n) {
+    ApiTrace tr__(ctx, "ltr_cloud_download");
     DevCloud* dc;
     LTR_TRY(cloud_get(ctx, c, &dc));
     if (n) *n = dc->n;
@@ -254,12 +290,14 @@ int ltr_cloud_download(ltr_ctx* ctx, ltr_cloud c, float* xyzi, int64_t capacity,
     return download_points(ctx, *dc, xyzi);
 }
 int ltr_cloud_free(ltr_ctx* ctx, ltr_cloud c) {
+    ApiTrace tr__(ctx, "ltr_cloud_free");
     DevCloud* dc;
     LTR_TRY(cloud_get(ctx, c, &dc));
     cloud_release(ctx, dc);
     return LTR_OK;
 }
 int ltr_cloud_copy(ltr_ctx* ctx, ltr_cloud src, ltr_cloud* out) {
+    ApiTrace tr__(ctx, "ltr_cloud_copy");
     DevCloud* s;
     LTR_TRY(cloud_get(ctx, src, &s));
     const DevCloud sc = *s;
@@ -271,6 +309,7 @@ int ltr_cloud_copy(ltr_ctx* ctx, ltr_cloud src, ltr_cloud* out) {
     return LTR_OK;
 }
 int ltr_cloud_concat(ltr_ctx* ctx, ltr_cloud a, ltr_cloud b, ltr_cloud* out) {
+    ApiTrace tr__(ctx, "ltr_cloud_concat");
     DevCloud *pa, *pb;
     LTR_TRY(cloud_get(ctx, a, &pa));
     LTR_TRY(cloud_get(ctx, b, &pb));
@@ -293,6 +332,7 @@ int ltr_cloud_device_ptrs(ltr_ctx* ctx, ltr_cloud c, float** x, float** y, float
 }
 
 int ltr_scanset_upload(ltr_ctx* ctx, const float* xyzi, const int64_t* offsets, int32_t K, ltr_scanset* out) {
+    ApiTrace tr__(ctx, "ltr_scanset_upload");
     if (!ctx || !out || !offsets || K < 0) return fail(ctx, LTR_ERR_INVALID, "bad argument");
     std::vector<int64_t> off(offsets, offsets + K + 1);
     if (off[K] > 0 && !xyzi) return fail(ctx, LTR_ERR_INVALID, "null points");
@@ -315,6 +355,7 @@ int ltr_scanset_download(ltr_ctx* ctx, ltr_scanset s, float* xyzi, int64_t capac
     return download_points(ctx, ss->pts, xyzi);
 }
 int ltr_scanset_free(ltr_ctx* ctx, ltr_scanset s) {
+    ApiTrace tr__(ctx, "ltr_scanset_free");
     DevScanSet* ss;
     LTR_TRY(scanset_get(ctx, s, &ss));
     cloud_release(ctx, &ss->pts);
@@ -323,6 +364,7 @@ int ltr_scanset_free(ltr_ctx* ctx, ltr_scanset s) {
     return LTR_OK;
 }
 int ltr_scanset_flatten(ltr_ctx* ctx, ltr_scanset s, ltr_cloud* out) {
+    ApiTrace tr__(ctx, "ltr_scanset_flatten");
     DevScanSet* ss;
     LTR_TRY(scanset_get(ctx, s, &ss));
     const DevCloud sc = ss->pts;
@@ -332,6 +374,7 @@ int ltr_scanset_flatten(ltr_ctx* ctx, ltr_scanset s, ltr_cloud* out) {
     return LTR_OK;
 }
 int ltr_scanset_concat_per_keyframe(ltr_ctx* ctx, ltr_scanset a, ltr_scanset b, ltr_scanset* out) {
+    ApiTrace tr__(ctx, "ltr_scanset_concat_per_keyframe");
     DevScanSet *pa, *pb;
     LTR_TRY(scanset_get(ctx, a, &pa));
     LTR_TRY(scanset_get(ctx, b, &pb));
@@ -352,6 +395,7 @@ int ltr_scanset_concat_per_keyframe(ltr_ctx* ctx, ltr_scanset a, ltr_scanset b, 
 }
 
 int ltr_poses_upload(ltr_ctx* ctx, const double* poses, const double* inv_poses, int32_t K, ltr_poses* out) {
+    ApiTrace tr__(ctx, "ltr_poses_upload");
     if (!ctx || !out || K < 0 || (K > 0 && (!poses || !inv_poses))) return fail(ctx, LTR_ERR_INVALID, "bad argument");
     int slot = -1;
     for (size_t i = 0; i < ctx->poses.size(); ++i) if (!ctx->poses[i].used) { slot = (int)i; break; }
@@ -367,7 +411,13 @@ int ltr_poses_upload(ltr_ctx* ctx, const double* poses, const double* inv_poses,
     LTR_TRY(dev_alloc(ctx, &d, (size_t)K * 24 * sizeof(double)));
     p.d = (double*)d;
     if (K > 0) LTR_CUDA(ctx, cudaMemcpyAsync(p.d, p.h.data(), (size_t)K * 24 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->poses[slot] = p;  // p.h (the source of the async copy) must stay alive: it now lives in the table
+    p.h_fast.resize((size_t)K * 16);
+    for (int k = 0; k < K; ++k) make_kf_fast(&p.h[(size_t)k * 24], ctx->cfg.base2lidar, ctx->ext_identity, &p.h_fast[(size_t)k * 16]);
+    LTR_TRY(dev_alloc(ctx, &d, (size_t)K * 16 * sizeof(float)));
+    p.d_fast = (float*)d;
+    if (K > 0) LTR_CUDA(ctx, cudaMemcpyAsync(p.d_fast, p.h_fast.data(), (size_t)K * 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->poses[slot] = p;
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = slot;
     return LTR_OK;
@@ -376,6 +426,7 @@ int ltr_poses_free(ltr_ctx* ctx, ltr_poses h) {
     DevPoses* p;
     LTR_TRY(poses_get(ctx, h, &p));
     dev_free(ctx, p->d);
+    dev_free(ctx, p->d_fast);
     *p = DevPoses();
     return LTR_OK;
 }
@@ -397,6 +448,16 @@ int ltr_profile_reset(ltr_ctx* ctx) {
     return LTR_OK;
 }
 
+int ltr_trace_dump(ltr_ctx* ctx, int reset) {
+    if (!ctx) return LTR_ERR_INVALID;
+    double tot = 0;
+    for (auto& kv : ctx->trace_acc) tot += kv.second.first;
+    fprintf(stderr, "[ltr trace] total %.2f ms in %zu entry points\n", tot * 1e3, ctx->trace_acc.size());
+    for (auto& kv : ctx->trace_acc) fprintf(stderr, "[ltr trace] %-36s calls %6ld  %10.3f ms\n", kv.first.c_str(), kv.second.second, kv.second.first * 1e3);
+    if (reset) ctx->trace_acc.clear();
+    return LTR_OK;
+}
+
 int ltr_timer_start(ltr_ctx* ctx) {
     if (!ctx) return LTR_ERR_INVALID;
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev_timer0, ctx->stream));
@@ -414,7 +475,7 @@ int ltr_timer_stop(ltr_ctx* ctx, double* ms) {
 
 int ltr_last_pass_stats(ltr_ctx* ctx, double* s) {
     if (!ctx || !s) return LTR_ERR_INVALID;
-    for (int i = 0; i < 5; ++i) s[i] = ctx->stats[i];
+    for (int i = 0; i < 6; ++i) s[i] = ctx->stats[i];
     return LTR_OK;
 }
 

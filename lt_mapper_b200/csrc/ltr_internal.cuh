@@ -5,6 +5,8 @@
 #include <string>
 #include <vector>
 #include <cstdio>
+#include <map>
+#include <chrono>
 #include "../../include/ltr_b200.h"
 
 namespace ltr {
@@ -32,6 +34,8 @@ struct DevScanSet {
 struct DevPoses {
     double* d = nullptr;
     std::vector<double> h;
+    float* d_fast = nullptr;       // K x 16 floats (KfFast, project_fast.cuh)
+    std::vector<float> h_fast;
     int K = 0;
     bool used = false;
 };
@@ -53,12 +57,14 @@ struct ltr_ctx {
     int64_t launches = 0;
     bool ext_identity = true;     // base2lidar/lidar2base exactly identity -> second transform step is exact and skipped
     double* d_ext = nullptr;      // 24 doubles: base2lidar rows 0..2, lidar2base rows 0..2
-    double stats[5] = {0, 0, 0, 0, 0};
+    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long* d_counters = nullptr;  // 4 device counters for pass statistics
     // per-kernel profile of the dominant kernel (map projection): CUDA-event time, launches, algorithmic bytes
     std::vector<cudaEvent_t> ev_pool;          // pairs
     int ev_used = 0;
-    double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // [0] remove-pass map kernel us, [1] launches, [2] algorithmic bytes, [3] point-projections
+    double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool trace = false;                        // LTR_TRACE=1: per-entry-point synchronised host timings, dumped at ltr_destroy
+    std::map<std::string, std::pair<double, long>> trace_acc; // [0] remove-pass map kernel us, [1] launches, [2] algorithmic bytes, [3] point-projections
                                                // [4] parse map kernel us, [5] launches, [6] algorithmic bytes, [7] point-projections
 };
 
@@ -88,6 +94,14 @@ int fail(ltr_ctx* ctx, int code, const char* fmt, ...);
         if (e__ != cudaSuccess) return ::ltr::fail(ctx, LTR_ERR_CUDA, "kernel launch failed: %s (%s:%d)", \
                                                    cudaGetErrorString(e__), __FILE__, __LINE__);      \
     } while (0)
+
+// per-entry-point host timing (only when LTR_TRACE=1; adds two stream synchronisations per call)
+struct ApiTrace {
+    ltr_ctx* c; const char* name; double t0;
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    ApiTrace(ltr_ctx* ctx, const char* n) : c(ctx), name(n), t0(0) { if (c && c->trace) { cudaStreamSynchronize(c->stream); t0 = now(); } }
+    ~ApiTrace() { if (c && c->trace) { cudaStreamSynchronize(c->stream); auto& a = c->trace_acc[name]; a.first += now() - t0; a.second += 1; } }
+};
 
 // allocation helpers (stream-ordered)
 int dev_alloc(ltr_ctx* ctx, void** p, size_t bytes);

@@ -11,7 +11,9 @@
 // index among equal ranges) is obtained here with one 64-bit atomicMin on (float_bits(range) << 32 | index).
 #include "ltr_internal.cuh"
 #include "ref_math.cuh"
+#include "project_fast.cuh"
 #include <algorithm>
+#include <cmath>
 
 namespace ltr {
 
@@ -178,6 +180,52 @@ static inline void prof_collect(ltr_ctx* ctx, int slot, double bytes_per_launch_
     ctx->ev_used = 0;
 }
 
+// 1 iff no map point can be >= 8000 m away from any keyframe origin in [k0, k1): then a pixel without a scan return
+// (scan range 10000) has scan - map > 200 for every map point and can never flag (see project_fast.cuh).
+static int empty_scan_shortcut_ok(ltr_ctx* ctx, const DevCloud& map, const DevPoses& poses, int k0, int k1, int* ok) {
+    *ok = 0;
+    float mn[3], mx[3];
+    LTR_TRY(minmax_xyz(ctx, map, mn, mx));
+    double worst = 0.0;
+    for (int k = k0; k < k1; ++k) {
+        const float* f = &poses.h_fast[(size_t)k * 16];
+        if (f[15] == 0.0f) return LTR_OK;
+        double d2 = 0.0;
+        for (int d = 0; d < 3; ++d) {
+            const double c = (double)f[9 + d];  // c_hi (the f32 part of the sensor origin is plenty for a 7 km bound)
+            const double e = std::max(std::fabs(c - (double)mn[d]), std::fabs(c - (double)mx[d]));
+            d2 += e * e;
+        }
+        worst = std::max(worst, d2);
+    }
+    *ok = (worst < 7000.0 * 7000.0) ? 1 : 0;
+    return LTR_OK;
+}
+
+__global__ void debug_fast_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ kf, const double* __restrict__ pose,
+                                  const double* __restrict__ ext, int ext_identity, int order, ImgShape g, FastCfg fc,
+                                  float* __restrict__ out /* n x 8: vcol_f vrow_f r_f rho_inv_r | vcol_e vrow_e r_e unused */) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    const FastProj f = fast_project(kf, x, y, z);
+    out[8 * i + 0] = __fmaf_rn(f.az, fc.col_scale, fc.col_off);
+    out[8 * i + 1] = __fmaf_rn(-f.el, fc.row_scale, fc.row_off);
+    out[8 * i + 2] = f.r;
+    out[8 * i + 3] = f.rho_inv_r;
+    float lx, ly, lz;
+    transform_point(pose, order, x, y, z, &lx, &ly, &lz);
+    if (!ext_identity) transform_point(ext, order, lx, ly, lz, &lx, &ly, &lz);
+    const Sph s = cart2sph(lx, ly, lz);
+    // the reference's pre-round floats (utility.cpp:122-123)
+    out[8 * i + 4] = fm((float)g.cols, fd(fa(rad2deg(s.az), fd(g.hfov, 2.0f)), fs(g.hfov, 0.0f)));
+    out[8 * i + 5] = fm((float)g.rows, fs(1.0f, fd(fa(rad2deg(s.el), fd(g.vfov, 2.0f)), fs(g.vfov, 0.0f))));
+    out[8 * i + 6] = s.r;
+    out[8 * i + 7] = 0.0f;
+}
+
+static inline size_t fast_smem_bytes(int nb) { return (size_t)((nb * 16 + 3) & ~3) * sizeof(float) + (size_t)(kFastThreads / 32) * 2 * kQueueCap * sizeof(uint64_t); }
+
 static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, max_blocks));
 }
@@ -190,6 +238,7 @@ extern "C" {
 
 int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_poses poses_h, int32_t kf_begin, int32_t kf_end,
                     int32_t mode, float res_alpha, float diff_thres, int32_t accumulate, int64_t* n_dynamic) {
+    ApiTrace tr__(ctx, "ltr_remove_pass");
     if (!ctx) return LTR_ERR_INVALID;
     DevCloud* map;
     DevScanSet* scans;
@@ -210,14 +259,20 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     const int64_t npx = (int64_t)rows * cols;
     const int B = std::max(1, std::min(ctx->cfg.keyframe_batch, kf_end - kf_begin));
     const bool cand = (mode != LTR_MODE_ND);
+    const bool use_fast = ctx->cfg.fast_path && npx <= (1 << 18) && B <= (1 << 12);   // queue-entry field widths, 32-bit pixel offsets (project_fast.cuh)
+    int shortcut = 0;
+    if (use_fast && cand && map->n > 0 && kf_end > kf_begin) LTR_TRY(empty_scan_shortcut_ok(ctx, *map, *poses, kf_begin, kf_end, &shortcut));
+    const FastCfg fc = make_fast_cfg(rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, shortcut);
+    if (use_fast) LTR_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     std::vector<int> launch_units;
     ctx->ev_used = 0;
     if (map->n > 0 && kf_end > kf_begin) {
         void *p_rimg, *p_win;
-        LTR_TRY(dev_alloc(ctx, &p_rimg, (size_t)B * npx * sizeof(uint32_t)));
+        LTR_TRY(dev_alloc(ctx, &p_rimg, (size_t)B * npx * sizeof(uint32_t) * (use_fast ? 2 : 1)));
         LTR_TRY(dev_alloc(ctx, &p_win, (size_t)B * npx * sizeof(uint64_t)));
         uint32_t* rimg = (uint32_t*)p_rimg;
+        uint32_t* amin = rimg + (size_t)B * npx;   // approximate running minimum (fast path only)
         uint64_t* win = (uint64_t*)p_win;
         const int fill_blocks = ctx->sm_count * 8;
         fill_u64_kernel<<<grid_for(B * npx, 256, fill_blocks), 256, 0, ctx->stream>>>(win, cand ? kWinNone : kWinEmpty, B * npx);
@@ -226,19 +281,32 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
             const int nb = std::min(B, kf_end - k0);
             fill_u32_kernel<<<grid_for(nb * npx, 256, fill_blocks), 256, 0, ctx->stream>>>(rimg, kNoPointBits, nb * npx);
             LTR_LAUNCH_CHECK(ctx);
+            if (use_fast) {
+                fill_u32_kernel<<<grid_for(nb * npx, 256, fill_blocks), 256, 0, ctx->stream>>>(amin, 0x7f800000u, nb * npx);
+                LTR_LAUNCH_CHECK(ctx);
+            }
             const int64_t npts = scans->h_off[k0 + nb] - scans->h_off[k0];
             if (npts > 0) {
                 scan_rimg_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, k0, nb, g, rimg);
                 LTR_LAUNCH_CHECK(ctx);
             }
-            const unsigned mb = (unsigned)((map->n + 255) / 256);
-            const size_t smem = (size_t)nb * 12 * sizeof(double);
             prof_begin(ctx);
             launch_units.push_back(nb);
-            if (cand) map_project_kernel<true><<<mb, 256, smem, ctx->stream>>>(view(*map), poses->d, k0, nb, ctx->d_ext, ctx->ext_identity ? 1 : 0,
-                                                                             ctx->cfg.transform_order, g, rimg, diff_thres, win);
-            else map_project_kernel<false><<<mb, 256, smem, ctx->stream>>>(view(*map), poses->d, k0, nb, ctx->d_ext, ctx->ext_identity ? 1 : 0,
-                                                                          ctx->cfg.transform_order, g, rimg, diff_thres, win);
+            if (use_fast) {
+                const unsigned fb = (unsigned)((map->n + kFastThreads * kFastPts - 1) / (kFastThreads * kFastPts));
+                const size_t fsmem = fast_smem_bytes(nb);
+                if (cand) map_project_fast_kernel<true><<<fb, kFastThreads, fsmem, ctx->stream>>>(view(*map), poses->d_fast, poses->d, k0, nb, ctx->d_ext,
+                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, diff_thres, win, amin, ctx->d_counters);
+                else map_project_fast_kernel<false><<<fb, kFastThreads, fsmem, ctx->stream>>>(view(*map), poses->d_fast, poses->d, k0, nb, ctx->d_ext,
+                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, diff_thres, win, amin, ctx->d_counters);
+            } else {
+                const unsigned mb = (unsigned)((map->n + 255) / 256);
+                const size_t smem = (size_t)nb * 12 * sizeof(double);
+                if (cand) map_project_kernel<true><<<mb, 256, smem, ctx->stream>>>(view(*map), poses->d, k0, nb, ctx->d_ext, ctx->ext_identity ? 1 : 0,
+                                                                                 ctx->cfg.transform_order, g, rimg, diff_thres, win);
+                else map_project_kernel<false><<<mb, 256, smem, ctx->stream>>>(view(*map), poses->d, k0, nb, ctx->d_ext, ctx->ext_identity ? 1 : 0,
+                                                                              ctx->cfg.transform_order, g, rimg, diff_thres, win);
+            }
             prof_end(ctx);
             LTR_LAUNCH_CHECK(ctx);
             const unsigned rb = (unsigned)((nb * npx + 255) / 256);
@@ -257,11 +325,20 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     prof_collect(ctx, 0, 12.0 * (double)map->n + (double)map->n / 8.0, (double)map->n, launch_units);
     ctx->stats[0] = (double)map->n * (kf_end - kf_begin);
     ctx->stats[1] = 0; ctx->stats[2] = ctx->stats[0]; ctx->stats[3] = 0;
+    if (use_fast) {
+        unsigned long long c[3] = {0, 0, 0};
+        LTR_CUDA(ctx, cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        ctx->stats[2] = (double)c[0] + (double)c[2];  // pairs that needed exact arithmetic (range-only + full)
+        ctx->stats[1] = ctx->stats[0] - ctx->stats[2];
+        ctx->stats[3] = (double)c[1];
+        ctx->stats[5] = (double)c[2];                 // pairs through the FULL exact path
+    }
     ctx->stats[4] = (double)ms * 1000.0;
     return LTR_OK;
 }
 
 int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_t kf_begin, int32_t kf_end, float res_alpha, ltr_scanset* out) {
+    ApiTrace tr__(ctx, "ltr_parse_projected");
     if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
     DevCloud* map;
     DevPoses* poses;
@@ -278,14 +355,19 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
     const DevCloud mapc = *map;
     const DevPoses posc = *poses;
     std::vector<int64_t> off((size_t)K + 1, 0);
+    const FastCfg fc = make_fast_cfg(rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, 0);
+    const bool use_fast = ctx->cfg.fast_path && npx <= (1 << 18) && ctx->cfg.keyframe_batch <= (1 << 12);
+    if (use_fast) LTR_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     void *p_list = nullptr, *p_cnt = nullptr;
     std::vector<int> launch_units;
     ctx->ev_used = 0;
     if (K > 0 && mapc.n > 0) {
         const int B = std::max(1, std::min(ctx->cfg.keyframe_batch, K));
-        void* p_win;
+        void *p_win, *p_amin = nullptr;
         LTR_TRY(dev_alloc(ctx, &p_win, (size_t)B * npx * sizeof(uint64_t)));
+        if (use_fast) LTR_TRY(dev_alloc(ctx, &p_amin, (size_t)B * npx * sizeof(uint32_t)));
+        uint32_t* amin = (uint32_t*)p_amin;
         LTR_TRY(dev_alloc(ctx, &p_list, (size_t)K * npx * sizeof(uint32_t)));
         LTR_TRY(dev_alloc(ctx, &p_cnt, (size_t)K * sizeof(unsigned int)));
         uint64_t* win = (uint64_t*)p_win;
@@ -293,17 +375,26 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
         LTR_LAUNCH_CHECK(ctx);
         for (int k0 = 0; k0 < K; k0 += B) {
             const int nb = std::min(B, K - k0);
-            const unsigned mb = (unsigned)((mapc.n + 255) / 256);
             prof_begin(ctx);
             launch_units.push_back(nb);
-            map_project_kernel<false><<<mb, 256, (size_t)nb * 12 * sizeof(double), ctx->stream>>>(view(mapc), posc.d, kf_begin + k0, nb, ctx->d_ext,
-                ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, nullptr, 0.0f, win);
+            if (use_fast) {
+                fill_u32_kernel<<<grid_for(nb * npx, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(amin, 0x7f800000u, nb * npx);
+                LTR_LAUNCH_CHECK(ctx);
+                const unsigned fb = (unsigned)((mapc.n + kFastThreads * kFastPts - 1) / (kFastThreads * kFastPts));
+                map_project_fast_kernel<false><<<fb, kFastThreads, fast_smem_bytes(nb), ctx->stream>>>(view(mapc), posc.d_fast, posc.d, kf_begin + k0, nb, ctx->d_ext,
+                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, nullptr, 0.0f, win, amin, ctx->d_counters);
+            } else {
+                const unsigned mb = (unsigned)((mapc.n + 255) / 256);
+                map_project_kernel<false><<<mb, 256, (size_t)nb * 12 * sizeof(double), ctx->stream>>>(view(mapc), posc.d, kf_begin + k0, nb, ctx->d_ext,
+                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, nullptr, 0.0f, win);
+            }
             prof_end(ctx);
             LTR_LAUNCH_CHECK(ctx);
             parse_compact_kernel<<<nb, 1024, 0, ctx->stream>>>(win, (int)npx, (uint32_t*)p_list + (size_t)k0 * npx, (unsigned int*)p_cnt + k0);
             LTR_LAUNCH_CHECK(ctx);
         }
         dev_free(ctx, p_win);
+        dev_free(ctx, p_amin);
         std::vector<unsigned int> cnt((size_t)K);
         LTR_CUDA(ctx, cudaMemcpyAsync(cnt.data(), p_cnt, (size_t)K * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -325,6 +416,14 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
     prof_collect(ctx, 4, 12.0 * (double)mapc.n, (double)mapc.n, launch_units);
     ctx->stats[0] = (double)mapc.n * K;
     ctx->stats[1] = 0; ctx->stats[2] = ctx->stats[0]; ctx->stats[3] = 0;
+    if (use_fast) {
+        unsigned long long c[3] = {0, 0, 0};
+        LTR_CUDA(ctx, cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        ctx->stats[2] = (double)c[0] + (double)c[2];
+        ctx->stats[1] = ctx->stats[0] - ctx->stats[2];
+        ctx->stats[3] = (double)c[1];
+        ctx->stats[5] = (double)c[2];
+    }
     ctx->stats[4] = (double)ms * 1000.0;
     return LTR_OK;
 }
@@ -354,6 +453,33 @@ int ltr_debug_pixel_index(ltr_ctx* ctx, const float* xyz, int64_t n, int32_t row
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     dev_free(ctx, p);
     return LTR_OK;
+}
+
+int ltr_debug_fast_project(ltr_ctx* ctx, const float* xyz, int64_t n, const double* inv_pose16, float res_alpha, float* out8, float* margins4) {
+    if (!ctx || !xyz || !inv_pose16 || !out8 || n < 0) return fail(ctx, LTR_ERR_INVALID, "bad argument");
+    int32_t rows, cols;
+    ltr_reset_rimg_size(ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, res_alpha, &rows, &cols);
+    const ImgShape g{rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg};
+    const FastCfg fc = make_fast_cfg(rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, 0);
+    if (margins4) { margins4[0] = fc.m_col_a; margins4[1] = fc.m_col_b; margins4[2] = fc.m_row; margins4[3] = fc.m_r_rel; }
+    if (n == 0) return LTR_OK;
+    ltr_poses ph;
+    double id[16];
+    for (int i = 0; i < 16; ++i) id[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    LTR_TRY(ltr_poses_upload(ctx, id, inv_pose16, 1, &ph));
+    const DevPoses pp = ctx->poses[ph];
+    void* p;
+    LTR_TRY(dev_alloc(ctx, &p, (size_t)n * (3 + 8) * sizeof(float)));
+    float* d_xyz = (float*)p;
+    float* d_out = d_xyz + 3 * n;
+    LTR_CUDA(ctx, cudaMemcpyAsync(d_xyz, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    debug_fast_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, pp.d_fast, pp.d, ctx->d_ext, ctx->ext_identity ? 1 : 0,
+                                                                        ctx->cfg.transform_order, g, fc, d_out);
+    LTR_LAUNCH_CHECK(ctx);
+    LTR_CUDA(ctx, cudaMemcpyAsync(out8, d_out, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, p);
+    return ltr_poses_free(ctx, ph);
 }
 
 }  // extern "C"

@@ -439,6 +439,7 @@ using namespace ltr;
 extern "C" {
 
 int ltr_voxel_centroid(ltr_ctx* ctx, ltr_cloud in, float leaf, ltr_cloud* out) {
+    ApiTrace tr__(ctx, "ltr_voxel_centroid");
     if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
     DevCloud* c;
     LTR_TRY(cloud_get(ctx, in, &c));
@@ -452,6 +453,7 @@ int ltr_voxel_centroid(ltr_ctx* ctx, ltr_cloud in, float leaf, ltr_cloud* out) {
 }
 
 int ltr_voxel_centroid_per_keyframe(ltr_ctx* ctx, ltr_scanset in, float leaf, ltr_scanset* out) {
+    ApiTrace tr__(ctx, "ltr_voxel_centroid_per_keyframe");
     if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
     DevScanSet* s;
     LTR_TRY(scanset_get(ctx, in, &s));
@@ -482,6 +484,7 @@ int ltr_voxel_centroid_per_keyframe(ltr_ctx* ctx, ltr_scanset in, float leaf, lt
 }
 
 int ltr_merge_scans_global(ltr_ctx* ctx, ltr_scanset scans, ltr_poses poses, ltr_cloud* out) {
+    ApiTrace tr__(ctx, "ltr_merge_scans_global");
     if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
     DevScanSet* s;
     DevPoses* p;
@@ -500,6 +503,7 @@ int ltr_merge_scans_global(ltr_ctx* ctx, ltr_scanset scans, ltr_poses poses, ltr
 }
 
 int ltr_preclean(ltr_ctx* ctx, ltr_scanset scans, float radius, ltr_scanset* out) {
+    ApiTrace tr__(ctx, "ltr_preclean");
     if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
     DevScanSet* s;
     LTR_TRY(scanset_get(ctx, scans, &s));
@@ -544,6 +548,7 @@ int ltr_flags_upload(ltr_ctx* ctx, ltr_cloud map, const uint8_t* flags, int64_t 
 }
 
 int ltr_apply_partition(ltr_ctx* ctx, ltr_cloud map, ltr_cloud* out_static, ltr_cloud* out_dynamic) {
+    ApiTrace tr__(ctx, "ltr_apply_partition");
     if (!ctx || !out_static || !out_dynamic) return fail(ctx, LTR_ERR_INVALID, "null argument");
     DevCloud* c;
     LTR_TRY(cloud_get(ctx, map, &c));

@@ -206,7 +206,10 @@ class Removerter:
     def close(self):
         if getattr(self, "_h", None):
             self.ctx._h = None
-            host_lib().ltrh_destroy(self._h)
+            try:
+                host_lib().ltrh_destroy(self._h)
+            except TypeError:  # interpreter shutdown
+                pass
             self._h = None
 
     def __del__(self):

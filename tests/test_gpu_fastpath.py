@@ -1,0 +1,99 @@
+"""The fast rejection path (project_fast.cuh) never changes a result: margins dominate the measured deviation of the
+approximate arithmetic from the reference arithmetic, and flags / visible points are identical with it on and off."""
+import numpy as np
+import pytest
+
+import oracle
+import lt_mapper_b200 as ltr
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_pose(rng, big=False):
+    T = np.eye(4)
+    q = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    T[:3, :3] = q
+    T[:3, 3] = rng.uniform(-500, 500, 3) if big else rng.uniform(-60, 60, 3)
+    return T
+
+
+@pytest.mark.parametrize("alpha", [2.5, 3.0, 1.0])
+def test_margins_dominate_measured_deviation(alpha):
+    rng = np.random.default_rng(42)
+    worst = np.zeros(3)
+    with ltr.Context() as ctx:
+        for trial in range(6):
+            pose = _random_pose(rng, big=trial % 2 == 1)
+            inv = np.linalg.inv(pose)
+            n = 2_000_000
+            # points in the sensor frame with log-uniform range 0.5 .. 150 m, all directions, plus near-axis and near-seam sets
+            d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+            d[: n // 8, :2] *= 1e-3                                     # near the vertical axis (ill-conditioned azimuth)
+            d[n // 8: n // 4, 1] = rng.uniform(-1e-4, 1e-4, n // 8); d[n // 8: n // 4, 0] = -np.abs(d[n // 8: n // 4, 0])   # azimuth seam +-pi
+            r = np.exp(rng.uniform(np.log(0.5), np.log(150.0), n))[:, None]
+            local = d * r
+            world = (local @ pose[:3, :3].T + pose[:3, 3]).astype(np.float32)
+            out, mg = ctx.debug_fast_project(world, inv, alpha)
+            ok = np.isfinite(out).all(axis=1)
+            o = out[ok].astype(np.float64)
+            cols = ltr.reset_rimg_size(alpha)[1]
+            dcol = np.abs(o[:, 0] - o[:, 4]); dcol = np.minimum(dcol, cols - dcol)     # the seam wraps
+            m_col = mg[0] + mg[1] * o[:, 3]
+            m_row = mg[2]
+            m_r = mg[3] * o[:, 2] + 1e-5
+            worst = np.maximum(worst, [np.max(dcol / m_col), np.max(np.abs(o[:, 1] - o[:, 5]) / m_row), np.max(np.abs(o[:, 2] - o[:, 6]) / m_r)])
+            assert ok.mean() > 0.99
+    print("max deviation / margin (col, row, range):", worst)
+    assert (worst < 0.5).all(), worst
+
+
+@pytest.mark.parametrize("mode,alpha", [(ltr.MODE_HD, 2.5), (ltr.MODE_HD, 1.0), (ltr.MODE_PD, 2.5), (ltr.MODE_ND, 2.5)])
+def test_fast_path_equals_exact_path(small_pair, small_maps, mode, alpha):
+    c = small_pair[0]
+    m = small_maps[0] if mode == ltr.MODE_HD else small_maps[1][::5]
+    inv = oracle.inverse_poses(c.poses)
+    res = []
+    for fast in (False, True):
+        with ltr.Context(fast_path=fast, keyframe_batch=3) as ctx:
+            mh = ctx.cloud_upload(m)
+            ss = ctx.scanset_upload(c.xyzi, c.offsets)
+            ps = ctx.poses_upload(c.poses, inv)
+            n = ctx.remove_pass(mh, ss, ps, mode, alpha)
+            st = ctx.last_pass_stats()
+            vis = ctx.parse_projected(mh, ps, 0, c.K, 3.0)
+            st2 = ctx.last_pass_stats()
+            res.append((n, ctx.flags_download(mh), ctx.scanset_download(vis), st, st2))
+    assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][2][1], res[1][2][1]) and np.array_equal(res[0][2][0].view(np.uint32), res[1][2][0].view(np.uint32))
+    exp = oracle.remove_pass(m, c.xyzi, c.offsets, inv, mode, alpha)
+    assert np.array_equal(res[1][1], exp)
+    st, st2 = res[1][3], res[1][4]
+    print("remove pass: pairs %.3g exact-path share %.4f atomics %.3g | parse: exact-path share %.4f" % (st[0], st[2] / st[0], st[3], st2[2] / st2[0]))
+    if mode == ltr.MODE_HD:
+        assert st[2] / st[0] < 0.5
+
+
+def test_fast_path_with_extrinsic_and_order(small_pair):
+    """Non-identity LiDAR->base extrinsic (two-step transform) and the PCL>=1.10 summation order."""
+    c = small_pair[0].subset(0, 3)
+    l2b = np.eye(4)
+    a = 0.05
+    l2b[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+    l2b[:3, 3] = [0.3, -0.1, 0.2]
+    inv = oracle.inverse_poses(c.poses)
+    merged = np.concatenate([oracle.transform(oracle.transform(c.scan(k), l2b, 1), c.poses[k], 1) for k in range(c.K)])
+    m = oracle.voxel(merged, 0.1)
+    exp = oracle.remove_pass(m, c.xyzi, c.offsets, inv, oracle.MODE_HD, 2.5, lidar2base=l2b, order=1)
+    e_vis, _ = oracle.parse_projected(m, inv[1], 3.0, lidar2base=l2b, order=1)
+    for fast in (False, True):
+        with ltr.Context(lidar2base=l2b, base2lidar=oracle.inverse4x4(l2b), transform_order=1, fast_path=fast) as ctx:
+            mh = ctx.cloud_upload(m); ss = ctx.scanset_upload(c.xyzi, c.offsets); ps = ctx.poses_upload(c.poses, inv)
+            ctx.remove_pass(mh, ss, ps, ltr.MODE_HD, 2.5)
+            assert np.array_equal(ctx.flags_download(mh), exp)
+            pts, off = ctx.scanset_download(ctx.parse_projected(mh, ps, 1, 2, 3.0))
+            assert np.array_equal(pts.view(np.uint32), e_vis.view(np.uint32))
+            g = ctx.cloud_download(ctx.merge_scans_global(ss, ps))
+            assert np.array_equal(g.view(np.uint32), merged.view(np.uint32))
+    assert exp.sum() > 0
