@@ -170,12 +170,17 @@ class Context:
         self._ck(lib().ltr_cloud_size(self._h, c, ctypes.byref(n)))
         return n.value
 
-    def cloud_download(self, c):
+    def cloud_download(self, c, out=None):
+        """Downloads cloud `c` as (n, 4) float32.  `out` may be a caller-owned (capacity, 4) float32 array (e.g. pinned
+        host memory for a fast D2H); the returned array is then a view of its first n rows."""
         n = self.cloud_size(c)
-        out = np.empty((n, 4), np.float32)
+        if out is None:
+            out = np.empty((n, 4), np.float32)
+        elif out.dtype != np.float32 or out.ndim != 2 or out.shape[1] != 4 or len(out) < n or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array of shape (>= n, 4)")
         m = ctypes.c_int64()
-        self._ck(lib().ltr_cloud_download(self._h, c, out.ctypes.data, n, ctypes.byref(m)))
-        return out
+        self._ck(lib().ltr_cloud_download(self._h, c, out.ctypes.data, len(out), ctypes.byref(m)))
+        return out[:n]
 
     def cloud_free(self, c):
         self._ck(lib().ltr_cloud_free(self._h, c))

@@ -177,7 +177,7 @@ constexpr int kQueueCap = 160;   // per warp and kind: < 32 left over + 4 * 32 p
 // gather from the scan image (HD/PD) or from approx_min (ND / visible points), compare, done.  Rare pairs reserve a
 // queue slot with a shared-memory atomic (no ballots on the common path).
 template <bool kCandidatesOnly>
-__global__ void __launch_bounds__(kFastThreads) map_project_fast_kernel(PtrView map, const float* __restrict__ kf_fast, const double* __restrict__ poses,
+__global__ void __launch_bounds__(kFastThreads, 3) map_project_fast_kernel(PtrView map, const float* __restrict__ kf_fast, const double* __restrict__ poses,
                                                                         int kf0, int nb, const double* __restrict__ ext, int ext_identity, int order,
                                                                         ImgShape g, FastCfg fc, const uint32_t* __restrict__ scan_rimg, float thres,
                                                                         uint64_t* __restrict__ win, uint32_t* __restrict__ approx_min,

@@ -96,8 +96,24 @@ class TorchDistComm:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.backend = dist.get_backend(group)
         self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-        self._cb = (_ALLREDUCE(self._allreduce), _ALLGATHER_I64(self._allgather_i64), _ALLGATHERV(self._allgatherv))
+        self.trace = os.environ.get("LTR_COMM_TRACE") == "1"
+        self.stats = {"allreduce": [0, 0.0, 0], "allgather_i64": [0, 0.0, 0], "allgatherv": [0, 0.0, 0]}   # calls, seconds, bytes
+        self._cb = (_ALLREDUCE(self._timed("allreduce", self._allreduce)), _ALLGATHER_I64(self._timed("allgather_i64", self._allgather_i64)),
+                    _ALLGATHERV(self._timed("allgatherv", self._allgatherv)))
         self.struct = Comm(self.rank, self.world, None, *self._cb)
+
+    def _timed(self, name, fn):
+        import time
+
+        def wrapped(*a):
+            t0 = time.perf_counter()
+            rc = fn(*a)
+            st = self.stats[name]
+            st[0] += 1
+            st[1] += time.perf_counter() - t0
+            st[2] += int(a[2]) * (1 if name == "allreduce" else 4) if name != "allgather_i64" else 8
+            return rc
+        return wrapped
 
     def _tensor(self, ptr, n, typestr, dtype):
         if self.device.type == "cuda":
@@ -258,8 +274,8 @@ class Removerter:
         self._ck(host_lib().ltrh_scanset(self._h, name.encode(), sess, ctypes.byref(h)))
         return h.value
 
-    def cloud(self, name, sess=0):
-        return self.ctx.cloud_download(self.cloud_handle(name, sess))
+    def cloud(self, name, sess=0, out=None):
+        return self.ctx.cloud_download(self.cloud_handle(name, sess), out=out)
 
     def cloud_size(self, name, sess=0):
         return self.ctx.cloud_size(self.cloud_handle(name, sess))
