@@ -89,6 +89,23 @@ int32_t ltrh_log_count(ltrh_removerter* r);
 /* pass log (the counters the reference prints at Removerter.cpp:811-822, 897, 904): vals = n_map, n_dynamic, n_static_after, n_dynamic_after */
 int ltrh_log_get(ltrh_removerter* r, int32_t i, char* what, int32_t cap, int64_t* vals);
 
+/* ---- file-level helpers of the ltremovert node surface (lt_mapper_b200/csrc/host/io.h), used by apps/ltremovert_b200.cpp ---- */
+const char* ltrh_io_last_error(void);
+/* binary/ascii PCD with float32 x y z [intensity] (pcl::io::loadPCDFile at Session.cpp:275); returns the point count or -1 */
+int64_t ltrh_io_read_pcd(const char* path, float* xyzi, int64_t capacity);
+/* pcl::io::savePCDFileBinary<PointXYZI>; octree_layout: WIDTH 1 / HEIGHT n as set by octreeDownsampling (utility.cpp:217-218) */
+int ltrh_io_write_pcd(const char* path, const float* xyzi, int64_t n, int32_t octree_layout);
+/* pose file: one line of 12 or 16 numbers per scan (Session.cpp:102-114); returns the pose count or -1 */
+int32_t ltrh_io_read_poses(const char* path, double* poses16, int32_t capacity);
+/* Session::parseKeyframes(range, gap) (Session.cpp:138-174, including its skip-two quirk) */
+int32_t ltrh_io_parse_keyframes(int32_t num_scans, int32_t start_idx, int32_t end_idx, int32_t gap, int32_t* out, int32_t capacity);
+/* Session::parseKeyframesInROI (Session.cpp:230-263, 10 m) */
+int32_t ltrh_io_parse_keyframes_in_roi(const double* scan_poses16, int32_t n, const double* roi_poses16, int32_t m, int32_t gap, int32_t* out, int32_t capacity);
+/* pcl::VoxelGrid at load (Session.cpp:284-289) incl. the int32 overflow fallback that returns the input unchanged */
+int64_t ltrh_io_voxel_grid(const float* xyzi, int64_t n, float leaf, float* out, int64_t capacity, int32_t* overflowed);
+/* one key of a roslaunch-style yaml ("removert/key"): scalar text and/or numeric list */
+int ltrh_io_yaml_get(const char* path, const char* key, char* value, int32_t capacity, double* list, int32_t list_capacity, int32_t* list_n);
+
 #ifdef __cplusplus
 }
 #endif

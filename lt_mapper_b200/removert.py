@@ -42,7 +42,8 @@ class Comm(ctypes.Structure):
 
 HOST_EXPORTS = ["ltrh_params_default", "ltrh_create", "ltrh_destroy", "ltrh_last_error", "ltrh_set_comm", "ltrh_context",
                 "ltrh_load_session", "ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0", "ltrh_stage", "ltrh_cloud",
-                "ltrh_scanset", "ltrh_timing", "ltrh_log_count", "ltrh_log_get"]
+                "ltrh_scanset", "ltrh_timing", "ltrh_log_count", "ltrh_log_get", "ltrh_io_last_error", "ltrh_io_read_pcd", "ltrh_io_write_pcd",
+                "ltrh_io_read_poses", "ltrh_io_parse_keyframes", "ltrh_io_parse_keyframes_in_roi", "ltrh_io_voxel_grid", "ltrh_io_yaml_get"]
 
 
 def host_lib():
@@ -75,6 +76,16 @@ def host_lib():
     L.ltrh_timing.restype = ctypes.c_double
     L.ltrh_log_count.argtypes = [vp]
     L.ltrh_log_get.argtypes = [vp, i32, ctypes.c_char_p, i32, vp]
+    L.ltrh_io_last_error.restype = ctypes.c_char_p
+    L.ltrh_io_read_pcd.argtypes = [ctypes.c_char_p, vp, i64]
+    L.ltrh_io_read_pcd.restype = i64
+    L.ltrh_io_write_pcd.argtypes = [ctypes.c_char_p, vp, i64, i32]
+    L.ltrh_io_read_poses.argtypes = [ctypes.c_char_p, vp, i32]
+    L.ltrh_io_parse_keyframes.argtypes = [i32, i32, i32, i32, vp, i32]
+    L.ltrh_io_parse_keyframes_in_roi.argtypes = [vp, i32, vp, i32, i32, vp, i32]
+    L.ltrh_io_voxel_grid.argtypes = [vp, i64, ctypes.c_float, vp, i64, P(i32)]
+    L.ltrh_io_voxel_grid.restype = i64
+    L.ltrh_io_yaml_get.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, i32, vp, i32, P(i32)]
     _LIB = L
     return L
 
@@ -294,3 +305,61 @@ class Removerter:
             host_lib().ltrh_log_get(self._h, i, buf, 64, vals.ctypes.data)
             out.append((buf.value.decode(), *[int(v) for v in vals]))
         return out
+
+
+# ---- file-level helpers (include/ltr_removert.h ltrh_io_*): thin ctypes views used by tests and tools ----
+def read_pcd(path):
+    L = host_lib()
+    n = L.ltrh_io_read_pcd(path.encode(), None, 0)
+    if n < 0:
+        raise IOError(L.ltrh_io_last_error().decode())
+    out = np.empty((n, 4), np.float32)
+    L.ltrh_io_read_pcd(path.encode(), out.ctypes.data, n)
+    return out
+
+
+def write_pcd(path, xyzi, octree_layout=False):
+    x = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+    if host_lib().ltrh_io_write_pcd(path.encode(), x.ctypes.data, len(x), int(octree_layout)) != 0:
+        raise IOError(host_lib().ltrh_io_last_error().decode())
+
+
+def read_poses(path):
+    L = host_lib()
+    n = L.ltrh_io_read_poses(path.encode(), None, 0)
+    if n < 0:
+        raise IOError(L.ltrh_io_last_error().decode())
+    out = np.empty((n, 4, 4), np.float64)
+    L.ltrh_io_read_poses(path.encode(), out.ctypes.data, n)
+    return out
+
+
+def parse_keyframes(num_scans, start_idx, end_idx, gap):
+    out = np.empty(max(num_scans, 1), np.int32)
+    n = host_lib().ltrh_io_parse_keyframes(num_scans, start_idx, end_idx, gap, out.ctypes.data, len(out))
+    return out[:n].copy()
+
+
+def parse_keyframes_in_roi(scan_poses, roi_poses, gap):
+    a = np.ascontiguousarray(scan_poses, np.float64).reshape(-1, 16)
+    b = np.ascontiguousarray(roi_poses, np.float64).reshape(-1, 16)
+    out = np.empty(max(len(a), 1), np.int32)
+    n = host_lib().ltrh_io_parse_keyframes_in_roi(a.ctypes.data, len(a), b.ctypes.data, len(b), gap, out.ctypes.data, len(out))
+    return out[:n].copy()
+
+
+def voxel_grid(xyzi, leaf):
+    x = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+    out = np.empty((max(len(x), 1), 4), np.float32)
+    ov = ctypes.c_int32()
+    n = host_lib().ltrh_io_voxel_grid(x.ctypes.data, len(x), leaf, out.ctypes.data, len(out), ctypes.byref(ov))
+    return out[:n].copy(), bool(ov.value)
+
+
+def yaml_get(path, key):
+    buf = ctypes.create_string_buffer(4096)
+    lst = np.zeros(64, np.float64)
+    n = ctypes.c_int32()
+    if host_lib().ltrh_io_yaml_get(path.encode(), key.encode(), buf, 4096, lst.ctypes.data, 64, ctypes.byref(n)) != 0:
+        raise IOError(host_lib().ltrh_io_last_error().decode())
+    return buf.value.decode(), lst[:n.value].copy()

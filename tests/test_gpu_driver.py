@@ -1,0 +1,76 @@
+"""File-in/file-out drop-in: apps/ltremovert_b200 on a synthetic dataset on disk == the oracle pipeline on the same keyframes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from lt_mapper_b200 import removert
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "lt_mapper_b200", "ltremovert_b200")
+
+
+def _write_session(d, sess):
+    os.makedirs(d / "Scans", exist_ok=True)
+    with open(d / "poses.txt", "w") as f:
+        for k in range(sess.K):
+            removert.write_pcd(str(d / "Scans" / f"{k:06d}.pcd"), sess.scan(k))
+            f.write(" ".join(repr(float(v)) for v in sess.poses[k][:3].ravel()) + "\n")
+
+
+def test_driver_matches_oracle(tmp_path, small_pair):
+    c, q = small_pair
+    _write_session(tmp_path / "central", c)
+    _write_session(tmp_path / "query", q)
+    out = tmp_path / "out"
+    cfg = tmp_path / "params.yaml"
+    cfg.write_text(f"""removert:
+  saveMapPCD: true
+  save_pcd_directory: "{out}"
+  central_sess_scan_dir: "{tmp_path}/central/Scans/"
+  central_sess_pose_path: "{tmp_path}/central/poses.txt"
+  query_sess_scan_dir: "{tmp_path}/query/Scans/"
+  query_sess_pose_path: "{tmp_path}/query/poses.txt"
+  sequence_vfov: 50
+  sequence_hfov: 360
+  ExtrinsicLiDARtoPoseBase: [1.0, 0.0, 0.0, 0.0,
+                             0.0, 1.0, 0.0, 0.0,
+                             0.0, 0.0, 1.0, 0.0,
+                             0.0, 0.0, 0.0, 1.0]
+  keyframe_gap: 1
+  start_idx: 2
+  end_idx: 5
+  remove_resolution_list: [2.5]
+  downsample_voxel_size: 0.05
+  num_nn_points_within: 2
+  dist_nn_points_within: 0.01
+""")
+    r = subprocess.run([BIN, "--config", str(cfg)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # the same keyframe selection through the host helpers, then the oracle pipeline
+    kc = removert.parse_keyframes(c.K, 2, 5, 1)
+    assert list(kc) == [2, 3, 4, 5]
+    kq = removert.parse_keyframes_in_roi(q.poses, c.poses[kc], 1)
+    O = oracle.Removerter(num_knn=2, knn_thr=0.01)
+    for s, d, ks in ((0, c, kc), (1, q, kq)):
+        xyzi = np.concatenate([d.scan(k) for k in ks]); off = np.concatenate([[0], np.cumsum([len(d.scan(k)) for k in ks])])
+        poses = removert.read_poses(str(tmp_path / ("central" if s == 0 else "query") / "poses.txt"))[ks]
+        O.load_session(s, xyzi, off, poses, oracle.inverse_poses(poses))
+    O.run(step3=True)
+    for name in ["OriginalNoisyCentralMapGlobal", "central_sess_high_dyn", "query_sess_high_dyn", "union_map_queryside", "union_map_centralside",
+                 "pd_map", "nd_map", "strong_nd_map", "weak_nd_map", "strong_pd_map", "weak_pd_map", "updated_map", "updated_map_strong"]:
+        got = removert.read_pcd(str(out / (name + ".pcd")))
+        exp = O.cloud("saved:" + name)
+        assert got.shape == exp.shape and np.array_equal(got.view(np.uint32), exp.view(np.uint32)), name
+    for d, member in (("scans_updated", "keyframe_scans_updated_"), ("scans_updated_strong", "keyframe_scans_updated_strong_"), ("scans_pd", "keyframe_scans_pd_"),
+                      ("scans_pd_strong", "keyframe_scans_strong_pd_"), ("scans_nd_strong", "keyframe_scans_strong_nd_")):
+        files = sorted(os.listdir(out / d))
+        assert files == [f"{k:06d}.pcd" for k in kc]          # per-keyframe files keep the input scan's name (Removerter.cpp:1642-1645)
+        for i, fn in enumerate(files):
+            got = removert.read_pcd(str(out / d / fn))
+            exp = O.cloud(member, 0, i)
+            assert got.shape == exp.shape and np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (d, fn)
+    assert os.path.isdir(out / "map_static") and os.path.isdir(out / "map_dynamic")
