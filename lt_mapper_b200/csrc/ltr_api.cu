@@ -19,14 +19,60 @@ int fail(ltr_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
+// Caching allocator.  cudaMallocAsync's pool showed multi-millisecond stalls (pool growth / remapping) at unpredictable
+// points of a step; every allocation of this library is used on ctx->stream only, so a block freed by the host after the
+// kernels using it were enqueued can be re-issued immediately (stream order protects it).  Blocks are rounded to 512 B /
+// 2 MiB granules and recycled best-fit (at most 25 % + 2 MiB larger than requested); cudaMalloc only on a miss (warm-up).
+static size_t round_block(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    const size_t g = bytes >= (1u << 20) ? (size_t)(2u << 20) : (size_t)512;
+    return (bytes + g - 1) / g * g;
+}
 int dev_alloc(ltr_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
-    if (bytes == 0) bytes = 256;
-    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
-    if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? LTR_ERR_NOMEM : LTR_ERR_CUDA, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    const size_t want = round_block(bytes);
+    auto it = ctx->free_blocks.lower_bound(want);
+    if (it != ctx->free_blocks.end() && it->first <= want + want / 4 + (size_t)(2u << 20)) {
+        *p = it->second;
+        ctx->live_blocks[*p] = it->first;
+        ctx->cached_bytes -= it->first;
+        ctx->live_bytes += it->first;
+        ctx->free_blocks.erase(it);
+        return LTR_OK;
+    }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e == cudaErrorMemoryAllocation && !ctx->free_blocks.empty()) {   // give the cache back and retry once
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+        ctx->free_blocks.clear();
+        ctx->cached_bytes = 0;
+        e = cudaMalloc(p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, e == cudaErrorMemoryAllocation ? LTR_ERR_NOMEM : LTR_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    ctx->live_blocks[*p] = want;
+    ctx->live_bytes += want;
     return LTR_OK;
 }
-void dev_free(ltr_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+void dev_free(ltr_ctx* ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->live_blocks.find(p);
+    if (it == ctx->live_blocks.end()) return;
+    const size_t sz = it->second;
+    ctx->live_blocks.erase(it);
+    ctx->live_bytes -= sz;
+    ctx->free_blocks.emplace(sz, p);
+    ctx->cached_bytes += sz;
+    if (ctx->cached_bytes > ((size_t)48 << 30)) {   // bound the cache: drop everything that is not in use
+        cudaStreamSynchronize(ctx->stream);
+        for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+        ctx->free_blocks.clear();
+        ctx->cached_bytes = 0;
+    }
+}
 
 int cloud_new(ltr_ctx* ctx, int64_t n, ltr_cloud* out) {
     if (n < 0) return fail(ctx, LTR_ERR_INVALID, "negative cloud size");
@@ -217,11 +263,6 @@ int ltr_create(ltr_ctx** out, const ltr_config* cfg) {
     cudaEventCreate(&ctx->ev_timer1);
     ctx->ev_pool.resize(512);
     for (auto& e2 : ctx->ev_pool) cudaEventCreate(&e2);
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
     double ext[24];
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) { ext[r * 4 + c] = cfg->base2lidar[r * 4 + c]; ext[12 + r * 4 + c] = cfg->lidar2base[r * 4 + c]; }
     void* p;
@@ -246,6 +287,8 @@ void ltr_destroy(ltr_ctx* ctx) {
     dev_free(ctx, ctx->d_ext);
     dev_free(ctx, ctx->d_counters);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+    for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
     for (auto& e2 : ctx->ev_pool) cudaEventDestroy(e2);
     cudaEventDestroy(ctx->ev_timer0);
     cudaEventDestroy(ctx->ev_timer1);
