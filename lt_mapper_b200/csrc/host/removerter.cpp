@@ -210,9 +210,10 @@ int Removerter::makeGlobalMap() {
 // partitionCurrentMap / ForND / ForPD (:801-828, 771-799, 740-768)
 int Removerter::partitionCurrentMapGeneric(ltr_cloud map, Session& source, ltr_scanset scans, int mode, float res, const char* what,
                                            ltr_cloud* stat, ltr_cloud* dyn) {
-    int64_t n_map = 0, n_local = 0;
+    int64_t n_map = 0;
     CK(ltr_cloud_size(ctx, map, &n_map));
-    CK(ltr_remove_pass(ctx, map, scans, source.keyframe_poses_, 0, source.num_keyframes_, mode, res, 0.1f, 0, &n_local));
+    // n_dynamic is taken from the partition below (after the cross-rank flag union), so no count is requested here
+    CK(ltr_remove_pass(ctx, map, scans, source.keyframe_poses_, 0, source.num_keyframes_, mode, res, 0.1f, 0, nullptr));
     CK(reduce_flags(map));
     CK(ltr_apply_partition(ctx, map, stat, dyn));
     int64_t n_dyn = 0;

@@ -518,6 +518,16 @@ int ltr_timer_stop(ltr_ctx* ctx, double* ms) {
 
 int ltr_last_pass_stats(ltr_ctx* ctx, double* s) {
     if (!ctx || !s) return LTR_ERR_INVALID;
+    if (ctx->stats_counters_pending) {
+        unsigned long long c[3] = {0, 0, 0};
+        LTR_CUDA(ctx, cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+        LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats[2] = (double)c[0] + (double)c[2];  // pairs that needed exact arithmetic (range-only + full)
+        ctx->stats[1] = ctx->stats[0] - ctx->stats[2];
+        ctx->stats[3] = (double)c[1];
+        ctx->stats[5] = (double)c[2];                 // pairs through the FULL exact path
+        ctx->stats_counters_pending = false;
+    }
     for (int i = 0; i < 6; ++i) s[i] = ctx->stats[i];
     return LTR_OK;
 }

@@ -58,6 +58,7 @@ struct ltr_ctx {
     bool ext_identity = true;     // base2lidar/lidar2base exactly identity -> second transform step is exact and skipped
     double* d_ext = nullptr;      // 24 doubles: base2lidar rows 0..2, lidar2base rows 0..2
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool stats_counters_pending = false;       // d_counters of the last pass not yet folded into stats[]
     unsigned long long* d_counters = nullptr;  // 4 device counters for pass statistics
     // per-kernel profile of the dominant kernel (map projection): CUDA-event time, launches, algorithmic bytes
     std::vector<cudaEvent_t> ev_pool;          // pairs

@@ -325,14 +325,7 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     prof_collect(ctx, 0, 12.0 * (double)map->n + (double)map->n / 8.0, (double)map->n, launch_units);
     ctx->stats[0] = (double)map->n * (kf_end - kf_begin);
     ctx->stats[1] = 0; ctx->stats[2] = ctx->stats[0]; ctx->stats[3] = 0;
-    if (use_fast) {
-        unsigned long long c[3] = {0, 0, 0};
-        LTR_CUDA(ctx, cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
-        ctx->stats[2] = (double)c[0] + (double)c[2];  // pairs that needed exact arithmetic (range-only + full)
-        ctx->stats[1] = ctx->stats[0] - ctx->stats[2];
-        ctx->stats[3] = (double)c[1];
-        ctx->stats[5] = (double)c[2];                 // pairs through the FULL exact path
-    }
+    ctx->stats_counters_pending = use_fast;   // device counters are fetched lazily by ltr_last_pass_stats
     ctx->stats[4] = (double)ms * 1000.0;
     return LTR_OK;
 }
@@ -416,14 +409,7 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
     prof_collect(ctx, 4, 12.0 * (double)mapc.n, (double)mapc.n, launch_units);
     ctx->stats[0] = (double)mapc.n * K;
     ctx->stats[1] = 0; ctx->stats[2] = ctx->stats[0]; ctx->stats[3] = 0;
-    if (use_fast) {
-        unsigned long long c[3] = {0, 0, 0};
-        LTR_CUDA(ctx, cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
-        ctx->stats[2] = (double)c[0] + (double)c[2];
-        ctx->stats[1] = ctx->stats[0] - ctx->stats[2];
-        ctx->stats[3] = (double)c[1];
-        ctx->stats[5] = (double)c[2];
-    }
+    ctx->stats_counters_pending = use_fast;
     ctx->stats[4] = (double)ms * 1000.0;
     return LTR_OK;
 }

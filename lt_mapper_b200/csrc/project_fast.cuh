@@ -35,7 +35,7 @@ struct FastCfg {
 //   transform: |dq| <= ~6e-7 * r per component  -> azimuth 6e-7 * r/rho rad, elevation ~1e-6 rad
 //   atan (degree-8 minimax in a^2, approximate reciprocal): <= 3e-7 rad;  quadrant fix-ups <= 3e-7 rad
 //   reference's own float chain (rad2deg rounding, (x + H/2)/H, scaling): <= 4e-7 * C px
-// Margins are set >= 3x the measured maxima.
+// Margins are set >= 3x the measured maxima (measured: deviation / margin <= 0.26 / 0.23 / 0.21 for column / row / range).
 __host__ inline FastCfg make_fast_cfg(int rows, int cols, float vfov, float hfov, int empty_scan_shortcut) {
     FastCfg f;
     const double kPi = 3.14159265358979323846;
@@ -43,10 +43,10 @@ __host__ inline FastCfg make_fast_cfg(int rows, int cols, float vfov, float hfov
     const double ppr_r = (double)rows * 180.0 / (kPi * (double)vfov);
     f.col_scale = (float)ppr_c; f.col_off = 0.5f * (float)cols;
     f.row_scale = (float)ppr_r; f.row_off = 0.5f * (float)rows;
-    f.m_col_a = (float)(ppr_c * 3.0e-6 + (double)cols * 1.0e-6);
-    f.m_col_b = (float)(ppr_c * 3.0e-6);
-    f.m_row = (float)(ppr_r * 6.0e-6 + (double)rows * 1.0e-6);
-    f.m_r_rel = 4.0e-6f; f.m_r_abs = 1.0e-5f;
+    f.m_col_a = (float)(ppr_c * 1.2e-6 + (double)cols * 4.0e-7);
+    f.m_col_b = (float)(ppr_c * 1.2e-6);
+    f.m_row = (float)(ppr_r * 2.4e-6 + (double)rows * 4.0e-7);
+    f.m_r_rel = 2.0e-6f; f.m_r_abs = 5.0e-6f;
     f.empty_scan_shortcut = empty_scan_shortcut;
     return f;
 }

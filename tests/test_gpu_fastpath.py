@@ -42,11 +42,11 @@ def test_margins_dominate_measured_deviation(alpha):
             dcol = np.abs(o[:, 0] - o[:, 4]); dcol = np.minimum(dcol, cols - dcol)     # the seam wraps
             m_col = mg[0] + mg[1] * o[:, 3]
             m_row = mg[2]
-            m_r = mg[3] * o[:, 2] + 1e-5
+            m_r = mg[3] * o[:, 2] + 5e-6
             worst = np.maximum(worst, [np.max(dcol / m_col), np.max(np.abs(o[:, 1] - o[:, 5]) / m_row), np.max(np.abs(o[:, 2] - o[:, 6]) / m_r)])
             assert ok.mean() > 0.99
     print("max deviation / margin (col, row, range):", worst)
-    assert (worst < 0.5).all(), worst
+    assert (worst < 1.0 / 3.0).all(), worst   # margins >= 3x the largest measured deviation
 
 
 @pytest.mark.parametrize("mode,alpha", [(ltr.MODE_HD, 2.5), (ltr.MODE_HD, 1.0), (ltr.MODE_PD, 2.5), (ltr.MODE_ND, 2.5)])
