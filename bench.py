@@ -279,8 +279,17 @@ def main():
         k_us = prof[0] / max(prof[1], 1.0)
         k_bytes = prof[2] / max(prof[1], 1.0)
         achieved = (k_bytes / (k_us * 1e-6)) / 1e9 if k_us > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": "map_project_kernel (remove/revert pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        traffic, traffic_note = None, "no ncu capture committed"
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_note = (f"ncu --set full (profiles/r01_ncu_map_project_fast.md): dram__bytes_read+write per 32-keyframe launch on the N={tj['N']} map = "
+                            f"{tj['dram_bytes_per_launch'] / 1e6:.0f} MB vs {tj['algorithmic_bytes_per_launch'] / 1e6:.0f} MB algorithmic "
+                            "(the map tile is read once per 32 keyframes; images stay in L2) -> the kernel is instruction-issue bound, not DRAM bound")
+        roofline = {"bound": "hbm", "kernel": "map_project_fast_kernel<candidates> (remove/revert/PD passes; ND launches included)", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                     "launches_timed": int(prof[1]), "avg_launch_us": k_us, "algorithmic_bytes_per_launch": k_bytes,
                     "point_projections_per_s": prof[3] / (prof[0] * 1e-6) if prof[0] > 0 else 0.0,
                     "kernel_share_of_step": (prof[0] / args.steps) / (ms_step * 1e3),
