@@ -11,6 +11,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run by the driver with -m gpu)")
+    # the native libraries are built artefacts (git-ignored): build them once if this checkout has none yet
+    libs = [os.path.join(ROOT, "lt_mapper_b200", n) for n in ("libltr_b200.so", "libltr_removert.so", "ltremovert_b200")]
+    libs += [os.path.join(ROOT, "oracle", "liboracle.so"), os.path.join(ROOT, "synth", "libltr_synth.so")]
+    if not all(os.path.exists(p) for p in libs):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
