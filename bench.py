@@ -226,6 +226,8 @@ def main():
             stage_t[k] = stage_t.get(k, 0.0) + R.timing(k)
     ms_total = R.ctx.timer_stop()
     barrier()
+    if os.environ.get("LTR_ALLOC_STATS") == "1":
+        R.ctx.trace_dump(False)
     launches = R.ctx.kernel_launches() - l0
     clocks = sampler.stop()
     prof = R.ctx.profile_get()

@@ -61,7 +61,8 @@ typedef struct ltr_config {
     int32_t transform_order;      /* double summation order of pcl::transformPointCloud:
                                      0 = ((m00 x + m01 y) + m02 z) + m03 (PCL <= 1.9), 1 = ((m03 + m00 x) + m01 y) + m02 z (PCL >= 1.10 SSE2) */
     int32_t keyframe_batch;       /* keyframes projected per kernel launch (0 = default) */
-    int32_t fast_path;            /* 1 = enable the exactness-preserving fast rejection path (default), 0 = exact arithmetic for every point */
+    int32_t fast_path;            /* 0 = reference arithmetic for every (point, keyframe) pair; 1 = exactness-preserving fast rejection path;
+                                     2 = 1 + tile-level occlusion/range culling for the scan-minus-map variants (default) */
 } ltr_config;
 
 /* Fills cfg with the reference defaults (vfov 50, hfov 360, identity extrinsic, order 0). */
@@ -161,8 +162,9 @@ int ltr_debug_fast_project(ltr_ctx* ctx, const float* xyz /* n*3 */, int64_t n, 
 void ltr_reset_rimg_size(float vfov, float hfov, float alpha, int32_t* rows, int32_t* cols);
 /* Statistics of the last ltr_remove_pass / ltr_parse_projected: [0] (point, keyframe) pairs projected, [1] pairs settled by
  * the fast path alone, [2] pairs that needed exact arithmetic, [3] atomics on the winner image, [4] kernel time of the
- * pass in microseconds (CUDA events), [5] pairs that went through the FULL reference arithmetic. */
-int ltr_last_pass_stats(ltr_ctx* ctx, double* stats6);
+ * pass in microseconds (CUDA events), [5] pairs that went through the FULL reference arithmetic, [6] pairs skipped by tile culling
+ * (they are included in [1]). */
+int ltr_last_pass_stats(ltr_ctx* ctx, double* stats7);
 /* Accumulated CUDA-event profile of the dominant kernels since the last reset:
  * [0..3] map-projection kernel of ltr_remove_pass: total microseconds, launches, algorithmic bytes
  *        (sum over launches of keyframes_in_launch * (12 N + N/8)), point-projections;

@@ -117,7 +117,7 @@ class Context:
     """One GPU context (ltr_ctx).  Handles returned by its methods are plain ints."""
 
     def __init__(self, device=0, vfov=50.0, hfov=360.0, lidar2base=None, base2lidar=None, transform_order=0,
-                 keyframe_batch=0, fast_path=True):
+                 keyframe_batch=0, fast_path=True, cull=True):
         L = lib()
         cfg = Config()
         L.ltr_config_default(ctypes.byref(cfg))
@@ -132,7 +132,7 @@ class Context:
                 cfg.base2lidar[i] = b2l[i]
         cfg.transform_order = transform_order
         cfg.keyframe_batch = keyframe_batch
-        cfg.fast_path = 1 if fast_path else 0
+        cfg.fast_path = (2 if cull else 1) if fast_path else 0
         self._h = ctypes.c_void_p()
         rc = L.ltr_create(ctypes.byref(self._h), ctypes.byref(cfg))
         if rc != LTR_OK:
@@ -321,7 +321,7 @@ class Context:
         return out, mg
 
     def last_pass_stats(self):
-        s = np.zeros(6, np.float64)
+        s = np.zeros(7, np.float64)
         self._ck(lib().ltr_last_pass_stats(self._h, s.ctypes.data))
         return s
 

@@ -545,7 +545,7 @@ void ltrh_params_default(ltrh_params* p) {
     p->extract_high_dyn_knn = 1;
     p->transform_order = 0;
     p->keyframe_batch = 0;
-    p->fast_path = 1;
+    p->fast_path = 2;
 }
 
 int ltrh_create(ltrh_removerter** out, const ltrh_params* p) {

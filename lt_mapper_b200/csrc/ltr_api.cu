@@ -37,6 +37,8 @@ int dev_alloc(ltr_ctx* ctx, void** p, size_t bytes) {
         ctx->live_blocks[*p] = it->first;
         ctx->cached_bytes -= it->first;
         ctx->live_bytes += it->first;
+        if (ctx->live_bytes > ctx->peak_live_bytes) ctx->peak_live_bytes = ctx->live_bytes;
+        ctx->n_cache_hits++;
         ctx->free_blocks.erase(it);
         return LTR_OK;
     }
@@ -55,6 +57,8 @@ int dev_alloc(ltr_ctx* ctx, void** p, size_t bytes) {
     }
     ctx->live_blocks[*p] = want;
     ctx->live_bytes += want;
+    if (ctx->live_bytes > ctx->peak_live_bytes) ctx->peak_live_bytes = ctx->live_bytes;
+    ctx->n_cuda_malloc++;
     return LTR_OK;
 }
 void dev_free(ltr_ctx* ctx, void* p) {
@@ -67,6 +71,7 @@ void dev_free(ltr_ctx* ctx, void* p) {
     ctx->free_blocks.emplace(sz, p);
     ctx->cached_bytes += sz;
     if (ctx->cached_bytes > ((size_t)48 << 30)) {   // bound the cache: drop everything that is not in use
+        ctx->n_purges++;
         cudaStreamSynchronize(ctx->stream);
         for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
         ctx->free_blocks.clear();
@@ -229,7 +234,7 @@ void ltr_config_default(ltr_config* cfg) {
     for (int i = 0; i < 16; ++i) cfg->lidar2base[i] = cfg->base2lidar[i] = (i % 5 == 0) ? 1.0 : 0.0;
     cfg->transform_order = 0;
     cfg->keyframe_batch = 0;
-    cfg->fast_path = 1;
+    cfg->fast_path = 2;
 }
 
 int ltr_create(ltr_ctx** out, const ltr_config* cfg) {
@@ -495,6 +500,8 @@ int ltr_trace_dump(ltr_ctx* ctx, int reset) {
     if (!ctx) return LTR_ERR_INVALID;
     double tot = 0;
     for (auto& kv : ctx->trace_acc) tot += kv.second.first;
+    fprintf(stderr, "[ltr alloc] live %.2f GB (peak %.2f GB), cached %.2f GB in %zu blocks, cudaMalloc calls %ld, cache hits %ld, purges %ld\n", ctx->live_bytes / 1e9,
+            ctx->peak_live_bytes / 1e9, ctx->cached_bytes / 1e9, ctx->free_blocks.size(), ctx->n_cuda_malloc, ctx->n_cache_hits, ctx->n_purges);
     fprintf(stderr, "[ltr trace] total %.2f ms in %zu entry points\n", tot * 1e3, ctx->trace_acc.size());
     for (auto& kv : ctx->trace_acc) fprintf(stderr, "[ltr trace] %-36s calls %6ld  %10.3f ms\n", kv.first.c_str(), kv.second.second, kv.second.first * 1e3);
     if (reset) ctx->trace_acc.clear();
@@ -519,16 +526,17 @@ int ltr_timer_stop(ltr_ctx* ctx, double* ms) {
 int ltr_last_pass_stats(ltr_ctx* ctx, double* s) {
     if (!ctx || !s) return LTR_ERR_INVALID;
     if (ctx->stats_counters_pending) {
-        unsigned long long c[3] = {0, 0, 0};
+        unsigned long long c[4] = {0, 0, 0, 0};
         LTR_CUDA(ctx, cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
         LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->stats[2] = (double)c[0] + (double)c[2];  // pairs that needed exact arithmetic (range-only + full)
         ctx->stats[1] = ctx->stats[0] - ctx->stats[2];
         ctx->stats[3] = (double)c[1];
         ctx->stats[5] = (double)c[2];                 // pairs through the FULL exact path
+        ctx->stats[6] = (double)c[3];                 // pairs skipped by tile culling
         ctx->stats_counters_pending = false;
     }
-    for (int i = 0; i < 6; ++i) s[i] = ctx->stats[i];
+    for (int i = 0; i < 7; ++i) s[i] = ctx->stats[i];
     return LTR_OK;
 }
 

@@ -67,7 +67,8 @@ struct ltr_ctx {
     // caching device allocator (single stream => a freed block can be handed out again immediately, stream-ordered)
     std::multimap<size_t, void*> free_blocks;  // size -> block
     std::map<void*, size_t> live_blocks;       // block -> size
-    size_t cached_bytes = 0, live_bytes = 0;
+    size_t cached_bytes = 0, live_bytes = 0, peak_live_bytes = 0;
+    long n_cuda_malloc = 0, n_cache_hits = 0, n_purges = 0;
     bool trace = false;                        // LTR_TRACE=1: per-entry-point synchronised host timings, dumped at ltr_destroy
     std::map<std::string, std::pair<double, long>> trace_acc; // [0] remove-pass map kernel us, [1] launches, [2] algorithmic bytes, [3] point-projections
                                                // [4] parse map kernel us, [5] launches, [6] algorithmic bytes, [7] point-projections

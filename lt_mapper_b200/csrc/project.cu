@@ -14,6 +14,7 @@
 #include "project_fast.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 namespace ltr {
 
@@ -224,6 +225,13 @@ __global__ void debug_fast_kernel(const float* __restrict__ xyz, int64_t n, cons
     out[8 * i + 7] = 0.0f;
 }
 
+// persistent grid: 4 resident CTAs per SM (64 registers, ~22 KB shared memory each), never more CTAs than tiles need
+static inline unsigned fast_grid(const ltr_ctx* ctx, int64_t n) {
+    const int64_t tiles = (n + 32 * kFastPts - 1) / (32 * kFastPts);
+    const int64_t ctas = (tiles + kFastThreads / 32 - 1) / (kFastThreads / 32);
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)ctx->sm_count * 4));
+}
+
 static inline size_t fast_smem_bytes(int nb) { return (size_t)((nb * 16 + 3) & ~3) * sizeof(float) + (size_t)(kFastThreads / 32) * 2 * kQueueCap * sizeof(uint64_t); }
 
 static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
@@ -264,6 +272,27 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     if (use_fast && cand && map->n > 0 && kf_end > kf_begin) LTR_TRY(empty_scan_shortcut_ok(ctx, *map, *poses, kf_begin, kf_end, &shortcut));
     const FastCfg fc = make_fast_cfg(rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, shortcut);
     if (use_fast) LTR_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    // tile culling (project_cull.cuh): scan-minus-map variants only, one keyframe per lane -> launches of at most 32 keyframes
+    CullArgs ca;
+    std::memset(&ca, 0, sizeof(ca));
+    const bool use_cull = use_fast && cand && ctx->cfg.fast_path >= 2 && B <= 32 && map->n >= kTilePts;
+    void *p_tiles = nullptr, *p_pyr = nullptr;
+    if (use_cull) {
+        ca.enabled = 1;
+        ca.ntiles = (map->n + kTilePts - 1) / kTilePts;
+        unsigned off = 0;
+        for (int L = 1; L <= kPyrLevels; ++L) {
+            const int RL = (rows + (1 << L) - 1) >> L, CL = (cols + (1 << L) - 1) >> L;
+            ca.lvl_off[L] = off; ca.lvl_cols[L] = CL;
+            off += (unsigned)(RL * CL);
+        }
+        ca.pyr_stride = off;
+        LTR_TRY(dev_alloc(ctx, &p_tiles, (size_t)ca.ntiles * sizeof(float4)));
+        LTR_TRY(dev_alloc(ctx, &p_pyr, (size_t)B * ca.pyr_stride * sizeof(float)));
+        ca.tiles = (const float4*)p_tiles; ca.pyr = (const float*)p_pyr;
+        tile_sphere_kernel<<<(unsigned)((ca.ntiles * 32 + 255) / 256), 256, 0, ctx->stream>>>(view(*map), (float4*)p_tiles, ca.ntiles);
+        LTR_LAUNCH_CHECK(ctx);
+    }
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     std::vector<int> launch_units;
     ctx->ev_used = 0;
@@ -285,20 +314,28 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
                 fill_u32_kernel<<<grid_for(nb * npx, 256, fill_blocks), 256, 0, ctx->stream>>>(amin, 0x7f800000u, nb * npx);
                 LTR_LAUNCH_CHECK(ctx);
             }
+
             const int64_t npts = scans->h_off[k0 + nb] - scans->h_off[k0];
             if (npts > 0) {
                 scan_rimg_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, k0, nb, g, rimg);
                 LTR_LAUNCH_CHECK(ctx);
             }
+            if (use_cull) {
+                const float empty_value = shortcut ? -__builtin_huge_valf() : __builtin_huge_valf();   // empty scan pixel: never flags / unknown
+                scan_pyramid_kernel<<<(unsigned)nb, 1024, 0, ctx->stream>>>(rimg, nb, rows, cols, empty_value, ca, (float*)p_pyr);
+                LTR_LAUNCH_CHECK(ctx);
+            }
             prof_begin(ctx);
             launch_units.push_back(nb);
             if (use_fast) {
-                const unsigned fb = (unsigned)((map->n + kFastThreads * kFastPts - 1) / (kFastThreads * kFastPts));
+                const unsigned fb = fast_grid(ctx, map->n);
                 const size_t fsmem = fast_smem_bytes(nb);
+                unsigned int* work = (unsigned int*)(ctx->d_counters + 4);
+                LTR_CUDA(ctx, cudaMemsetAsync(work, 0, sizeof(unsigned int), ctx->stream));
                 if (cand) map_project_fast_kernel<true><<<fb, kFastThreads, fsmem, ctx->stream>>>(view(*map), poses->d_fast, poses->d, k0, nb, ctx->d_ext,
-                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, diff_thres, win, amin, ctx->d_counters);
+                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, diff_thres, win, amin, ca, ctx->d_counters, work);
                 else map_project_fast_kernel<false><<<fb, kFastThreads, fsmem, ctx->stream>>>(view(*map), poses->d_fast, poses->d, k0, nb, ctx->d_ext,
-                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, diff_thres, win, amin, ctx->d_counters);
+                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, diff_thres, win, amin, ca, ctx->d_counters, work);
             } else {
                 const unsigned mb = (unsigned)((map->n + 255) / 256);
                 const size_t smem = (size_t)nb * 12 * sizeof(double);
@@ -317,6 +354,8 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
         dev_free(ctx, p_rimg);
         dev_free(ctx, p_win);
     }
+    dev_free(ctx, p_tiles);
+    dev_free(ctx, p_pyr);
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     if (n_dynamic) LTR_TRY(count_flags(ctx, map->flags, map->n, n_dynamic));
     LTR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
@@ -373,9 +412,13 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
             if (use_fast) {
                 fill_u32_kernel<<<grid_for(nb * npx, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(amin, 0x7f800000u, nb * npx);
                 LTR_LAUNCH_CHECK(ctx);
-                const unsigned fb = (unsigned)((mapc.n + kFastThreads * kFastPts - 1) / (kFastThreads * kFastPts));
+                const unsigned fb = fast_grid(ctx, mapc.n);
+                CullArgs no_cull;
+                std::memset(&no_cull, 0, sizeof(no_cull));
+                unsigned int* work = (unsigned int*)(ctx->d_counters + 4);
+                LTR_CUDA(ctx, cudaMemsetAsync(work, 0, sizeof(unsigned int), ctx->stream));
                 map_project_fast_kernel<false><<<fb, kFastThreads, fast_smem_bytes(nb), ctx->stream>>>(view(mapc), posc.d_fast, posc.d, kf_begin + k0, nb, ctx->d_ext,
-                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, nullptr, 0.0f, win, amin, ctx->d_counters);
+                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, nullptr, 0.0f, win, amin, no_cull, ctx->d_counters, work);
             } else {
                 const unsigned mb = (unsigned)((mapc.n + 255) / 256);
                 map_project_kernel<false><<<mb, 256, (size_t)nb * 12 * sizeof(double), ctx->stream>>>(view(mapc), posc.d, kf_begin + k0, nb, ctx->d_ext,

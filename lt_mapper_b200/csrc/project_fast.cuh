@@ -165,6 +165,10 @@ __device__ __noinline__ void exact_full_pair(const PtrView& map, uint64_t e, con
     }
 }
 
+}  // namespace ltr
+#include "project_cull.cuh"
+namespace ltr {
+
 constexpr int kFastThreads = 256;
 constexpr int kFastPts = 4;      // map points per thread (registers), strided by the block size for coalescing
 constexpr int kQueueCap = 160;   // per warp and kind: < 32 left over + 4 * 32 pushed per keyframe step
@@ -177,11 +181,12 @@ constexpr int kQueueCap = 160;   // per warp and kind: < 32 left over + 4 * 32 p
 // gather from the scan image (HD/PD) or from approx_min (ND / visible points), compare, done.  Rare pairs reserve a
 // queue slot with a shared-memory atomic (no ballots on the common path).
 template <bool kCandidatesOnly>
-__global__ void __launch_bounds__(kFastThreads, 3) map_project_fast_kernel(PtrView map, const float* __restrict__ kf_fast, const double* __restrict__ poses,
+__global__ void __launch_bounds__(kFastThreads, 4) map_project_fast_kernel(PtrView map, const float* __restrict__ kf_fast, const double* __restrict__ poses,
                                                                         int kf0, int nb, const double* __restrict__ ext, int ext_identity, int order,
                                                                         ImgShape g, FastCfg fc, const uint32_t* __restrict__ scan_rimg, float thres,
                                                                         uint64_t* __restrict__ win, uint32_t* __restrict__ approx_min,
-                                                                        unsigned long long* __restrict__ counters) {
+                                                                        CullArgs ca, unsigned long long* __restrict__ counters,
+                                                                        unsigned int* __restrict__ work_counter) {
     extern __shared__ float s_dyn[];
     float* s_kf = s_dyn;                                                                    // nb * 16
     const int warp = threadIdx.x >> 5;
@@ -192,16 +197,6 @@ __global__ void __launch_bounds__(kFastThreads, 3) map_project_fast_kernel(PtrVi
     if ((threadIdx.x & 31) < 2) s_cnt[warp][threadIdx.x & 31] = 0;
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
-    const int64_t base = (int64_t)blockIdx.x * (kFastThreads * kFastPts) + threadIdx.x;
-    float px_[kFastPts], py_[kFastPts], pz_[kFastPts];
-    uint32_t pi_[kFastPts];
-#pragma unroll
-    for (int j = 0; j < kFastPts; ++j) {
-        // the last block re-processes point n-1 in its padding lanes: harmless (atomicMin of an identical key)
-        const int64_t i = min(base + (int64_t)j * kFastThreads, map.n - 1);
-        pi_[j] = (uint32_t)i;
-        px_[j] = map.x[i]; py_[j] = map.y[i]; pz_[j] = map.z[i];
-    }
     const uint32_t npx = (uint32_t)(g.rows * g.cols);
     const int hi_c = g.cols - 1, hi_r = g.rows - 1;
     // folded constants
@@ -210,8 +205,38 @@ __global__ void __launch_bounds__(kFastThreads, 3) map_project_fast_kernel(PtrVi
     const float thr_lo = thres - fc.m_r_abs, rel_m1 = fc.m_r_rel - 1.0f;
     const float mr2_rel = 2.0f * fc.m_r_rel, mr2_abs = 2.0f * fc.m_r_abs;
     const uint32_t empty_bits = fc.empty_scan_shortcut ? 0xff800000u : kNoPointBitsF;
-    unsigned n_a = 0, n_b = 0, n_atomics = 0;
+    unsigned n_a = 0, n_b = 0, n_atomics = 0, n_culled = 0;
+    // Persistent warps: each warp claims 128-point tiles from a global counter until the map is exhausted, so warps whose
+    // tiles are culled in many keyframes do not leave issue slots idle while their CTA-mates finish.
+    const long long total_tiles = (map.n + (32 * kFastPts) - 1) / (32 * kFastPts);
+    for (;;) {
+    unsigned tile_u = 0;
+    if (lane == 0) tile_u = atomicAdd(work_counter, 1u);
+    tile_u = __shfl_sync(0xffffffffu, tile_u, 0);
+    const long long tile = (long long)tile_u;
+    if (tile >= total_tiles) break;
+    // lane l holds points tile * 128 + 32 j + l, j = 0..3 (coalesced per j)
+    const int64_t base = (int64_t)tile * (32 * kFastPts) + lane;
+    float px_[kFastPts], py_[kFastPts], pz_[kFastPts];
+    uint32_t pi_[kFastPts];
+#pragma unroll
+    for (int j = 0; j < kFastPts; ++j) {
+        // the last tile re-processes point n-1 in its padding lanes: harmless (atomicMin of an identical key)
+        const int64_t i = min(base + (int64_t)j * 32, map.n - 1);
+        pi_[j] = (uint32_t)i;
+        px_[j] = map.x[i]; py_[j] = map.y[i]; pz_[j] = map.z[i];
+    }
+    // Tile culling (project_cull.cuh): lane l tests this 128-point tile against keyframe l of the launch; the ballot is the
+    // set of keyframes in which no point of the tile can be a candidate -- those iterations of the k loop are skipped.
+    unsigned cull_mask = 0u;
+    if (kCandidatesOnly && ca.enabled) {
+        const float4 t = ca.tiles[tile];
+        const bool c = ((int)lane < nb) && tile_culled(s_kf + 16 * lane, t, fc, g, ca, (int)lane, thres);
+        cull_mask = __ballot_sync(0xffffffffu, c);
+        if (lane == 0) n_culled += __popc(cull_mask);
+    }
     for (int k = 0; k < nb; ++k) {
+        if ((cull_mask >> k) & 1u) continue;   // warp-uniform
         float kf[16];
         {
             const float4* s4 = reinterpret_cast<const float4*>(s_kf + 16 * k);
@@ -273,6 +298,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) map_project_fast_kernel(PtrVi
         if (lane == 0) { s_cnt[warp][0] = qa; s_cnt[warp][1] = qb; }
         __syncwarp();
     }
+    }  // persistent tile loop
     const int qa = *(volatile int*)&s_cnt[warp][0], qb = *(volatile int*)&s_cnt[warp][1];
     if ((int)lane < qa) {
         exact_range_pair<kCandidatesOnly>(map, s_qa[lane], poses, kf0, ext, ext_identity, order, npx, scan_rimg, thres, win, fc.empty_scan_shortcut, &n_atomics);
@@ -282,12 +308,13 @@ __global__ void __launch_bounds__(kFastThreads, 3) map_project_fast_kernel(PtrVi
         exact_full_pair<kCandidatesOnly>(map, s_qb[lane], poses, kf0, ext, ext_identity, order, g, scan_rimg, thres, win, fc.empty_scan_shortcut, &n_atomics);
         ++n_b;
     }
-    // statistics: [0] pairs through the exact-range path, [1] atomics on the winner image, [2] pairs through the full exact path
+    // statistics: [0] pairs through the exact-range path, [1] atomics on the winner image, [2] pairs through the full exact path, [3] culled pairs
     for (int o = 16; o > 0; o >>= 1) {
         n_a += __shfl_down_sync(0xffffffffu, n_a, o); n_b += __shfl_down_sync(0xffffffffu, n_b, o); n_atomics += __shfl_down_sync(0xffffffffu, n_atomics, o);
     }
     if (lane == 0 && counters) {
         atomicAdd(&counters[0], (unsigned long long)n_a); atomicAdd(&counters[1], (unsigned long long)n_atomics); atomicAdd(&counters[2], (unsigned long long)n_b);
+        if (n_culled) atomicAdd(&counters[3], (unsigned long long)n_culled * (32ull * kFastPts));   // pairs skipped by tile culling
     }
 }
 

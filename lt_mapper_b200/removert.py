@@ -199,7 +199,7 @@ def selfremovert_schedule(resolutions):
 class Removerter:
     def __init__(self, device=0, vfov=50.0, hfov=360.0, lidar2base=None, num_knn=2, knn_thr=0.01, voxel=0.05,
                  schedule=((OP_REMOVE, 2.5),), extract_high_dyn_knn=True, transform_order=0, keyframe_batch=0,
-                 fast_path=True, comm=None):
+                 fast_path=True, cull=True, comm=None):
         L = host_lib()
         p = Params()
         L.ltrh_params_default(ctypes.byref(p))
@@ -215,7 +215,7 @@ class Removerter:
         for i, (op, res) in enumerate(schedule):
             p.schedule_op[i], p.schedule_res[i] = op, res
         p.extract_high_dyn_knn = int(extract_high_dyn_knn)
-        p.transform_order, p.keyframe_batch, p.fast_path = transform_order, keyframe_batch, int(fast_path)
+        p.transform_order, p.keyframe_batch, p.fast_path = transform_order, keyframe_batch, ((2 if cull else 1) if fast_path else 0)
         self._h = ctypes.c_void_p()
         rc = L.ltrh_create(ctypes.byref(self._h), ctypes.byref(p))
         if rc != 0:

@@ -55,8 +55,8 @@ def test_fast_path_equals_exact_path(small_pair, small_maps, mode, alpha):
     m = small_maps[0] if mode == ltr.MODE_HD else small_maps[1][::5]
     inv = oracle.inverse_poses(c.poses)
     res = []
-    for fast in (False, True):
-        with ltr.Context(fast_path=fast, keyframe_batch=3) as ctx:
+    for fast, cull in ((False, False), (True, False), (True, True)):
+        with ltr.Context(fast_path=fast, cull=cull, keyframe_batch=3) as ctx:
             mh = ctx.cloud_upload(m)
             ss = ctx.scanset_upload(c.xyzi, c.offsets)
             ps = ctx.poses_upload(c.poses, inv)
@@ -65,11 +65,15 @@ def test_fast_path_equals_exact_path(small_pair, small_maps, mode, alpha):
             vis = ctx.parse_projected(mh, ps, 0, c.K, 3.0)
             st2 = ctx.last_pass_stats()
             res.append((n, ctx.flags_download(mh), ctx.scanset_download(vis), st, st2))
-    assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1])
-    assert np.array_equal(res[0][2][1], res[1][2][1]) and np.array_equal(res[0][2][0].view(np.uint32), res[1][2][0].view(np.uint32))
+    for other in res[1:]:
+        assert res[0][0] == other[0] and np.array_equal(res[0][1], other[1])
+        assert np.array_equal(res[0][2][1], other[2][1]) and np.array_equal(res[0][2][0].view(np.uint32), other[2][0].view(np.uint32))
     exp = oracle.remove_pass(m, c.xyzi, c.offsets, inv, mode, alpha)
-    assert np.array_equal(res[1][1], exp)
-    st, st2 = res[1][3], res[1][4]
+    assert np.array_equal(res[2][1], exp)
+    st, st2 = res[2][3], res[2][4]
+    print("culled share %.3f" % (st[6] / st[0]))
+    if mode == ltr.MODE_ND:
+        assert st[6] == 0         # never culled: a far point can still win its pixel
     print("remove pass: pairs %.3g exact-path share %.4f atomics %.3g | parse: exact-path share %.4f" % (st[0], st[2] / st[0], st[3], st2[2] / st2[0]))
     if mode == ltr.MODE_HD:
         assert st[2] / st[0] < 0.5
@@ -87,8 +91,8 @@ def test_fast_path_with_extrinsic_and_order(small_pair):
     m = oracle.voxel(merged, 0.1)
     exp = oracle.remove_pass(m, c.xyzi, c.offsets, inv, oracle.MODE_HD, 2.5, lidar2base=l2b, order=1)
     e_vis, _ = oracle.parse_projected(m, inv[1], 3.0, lidar2base=l2b, order=1)
-    for fast in (False, True):
-        with ltr.Context(lidar2base=l2b, base2lidar=oracle.inverse4x4(l2b), transform_order=1, fast_path=fast) as ctx:
+    for fast, cull in ((False, False), (True, False), (True, True)):
+        with ltr.Context(lidar2base=l2b, base2lidar=oracle.inverse4x4(l2b), transform_order=1, fast_path=fast, cull=cull) as ctx:
             mh = ctx.cloud_upload(m); ss = ctx.scanset_upload(c.xyzi, c.offsets); ps = ctx.poses_upload(c.poses, inv)
             ctx.remove_pass(mh, ss, ps, ltr.MODE_HD, 2.5)
             assert np.array_equal(ctx.flags_download(mh), exp)

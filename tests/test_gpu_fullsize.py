@@ -28,8 +28,8 @@ def test_fast_equals_exact_and_oracle_spot_checks(big):
     assert len(m) > 5_000_000
     inv = np.stack([np.linalg.inv(p) for p in c.poses])
     flags = {}
-    for fast in (True, False):
-        with ltr.Context(fast_path=fast) as ctx:
+    for fast in (True, "nocull", False):
+        with ltr.Context(fast_path=bool(fast), cull=(fast is True)) as ctx:
             mh = ctx.cloud_upload(m); ss = ctx.scanset_upload(c.xyzi, c.offsets); ps = ctx.poses_upload(c.poses, inv)
             n = ctx.remove_pass(mh, ss, ps, ltr.MODE_HD, 2.5)
             f = ctx.flags_download(mh)
@@ -41,8 +41,8 @@ def test_fast_equals_exact_and_oracle_spot_checks(big):
             assert ctx.cloud_size(st) + ctx.cloud_size(dy) == len(m) and ctx.cloud_size(dy) == int(sub.sum())
             vis = ctx.parse_projected(mh, ps, 100, 102, 3.0)
             flags[fast] = (f, sub, ctx.scanset_download(vis))
-    assert np.array_equal(flags[True][0], flags[False][0])
-    assert np.array_equal(flags[True][1], flags[False][1])
+    assert np.array_equal(flags[True][0], flags[False][0]) and np.array_equal(flags["nocull"][0], flags[False][0])
+    assert np.array_equal(flags[True][1], flags[False][1]) and np.array_equal(flags["nocull"][1], flags[False][1])
     assert np.array_equal(flags[True][2][0].view(np.uint32), flags[False][2][0].view(np.uint32)) and np.array_equal(flags[True][2][1], flags[False][2][1])
     sl = slice(c.offsets[17], c.offsets[20])
     exp = oracle.remove_pass(m, c.xyzi[sl], c.offsets[17:21] - c.offsets[17], inv[17:20], oracle.MODE_HD, 2.5)
