@@ -1,0 +1,2 @@
+// Stand-in for <pcl/point_cloud.h> (not installed here): everything the ltremovert sources use lives in ltr_shim_core.h.
+#include "ltr_shim_core.h"

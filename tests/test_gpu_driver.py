@@ -74,3 +74,39 @@ def test_driver_matches_oracle(tmp_path, small_pair):
             exp = O.cloud(member, 0, i)
             assert got.shape == exp.shape and np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (d, fn)
     assert os.path.isdir(out / "map_static") and os.path.isdir(out / "map_dynamic")
+
+
+def test_driver_matches_compiled_reference(tmp_path, small_pair):
+    """The same dataset and parameters through (a) the reference's own Removerter::run(), compiled from /root/reference behind
+    the third-party stand-ins (oracle/_ref, prebuilt; see oracle/ref_shim), and (b) the drop-in binary: identical output trees."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libltremovert_ref.so not built")
+    c, q = small_pair
+    _write_session(tmp_path / "central", c)
+    _write_session(tmp_path / "query", q)
+    ext = [0.955336489125606, -0.29552020666133955, 0.0, 0.5, 0.29552020666133955, 0.955336489125606, 0.0, -0.2, 0.0, 0.0, 1.0, 1.1, 0.0, 0.0, 0.0, 1.0]
+    common = dict(sequence_vfov=50.0, sequence_hfov=360.0, keyframe_gap=2, start_idx=0, end_idx=5, downsample_voxel_size=0.05,
+                  num_nn_points_within=1, dist_nn_points_within=0.04)
+    out_ref, out_gpu = tmp_path / "out_ref", tmp_path / "out_gpu"
+    R = ref.Removerter(dict(common, saveMapPCD=True, save_pcd_directory=str(out_ref), ExtrinsicLiDARtoPoseBase=ext,
+                            central_sess_scan_dir=f"{tmp_path}/central/Scans/", central_sess_pose_path=f"{tmp_path}/central/poses.txt",
+                            query_sess_scan_dir=f"{tmp_path}/query/Scans/", query_sess_pose_path=f"{tmp_path}/query/poses.txt"))
+    R.run()
+    R.close()
+    cfg = tmp_path / "params.yaml"
+    cfg.write_text("removert:\n  saveMapPCD: true\n" + f'  save_pcd_directory: "{out_gpu}"\n'
+                   + f'  central_sess_scan_dir: "{tmp_path}/central/Scans/"\n  central_sess_pose_path: "{tmp_path}/central/poses.txt"\n'
+                   + f'  query_sess_scan_dir: "{tmp_path}/query/Scans/"\n  query_sess_pose_path: "{tmp_path}/query/poses.txt"\n'
+                   + "  ExtrinsicLiDARtoPoseBase: [" + ", ".join(repr(v) for v in ext) + "]\n"
+                   + "".join(f"  {k}: {v}\n" for k, v in common.items()))
+    r = subprocess.run([BIN, "--config", str(cfg)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+    def tree(d):
+        return sorted(os.path.relpath(os.path.join(p, f), d) for p, _, fs in os.walk(d) for f in fs)
+    files = tree(out_ref)
+    assert files == tree(out_gpu) and len(files) >= 14 + 5 * 3
+    for f in files:
+        a, b = removert.read_pcd(str(out_ref / f)), removert.read_pcd(str(out_gpu / f))
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), f
