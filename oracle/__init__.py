@@ -2,7 +2,9 @@
 
 ctypes front-end of the dependency-free CPU restatement of the LT-removert hot path (oracle.h).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
-this package; lt_mapper_b200 never does.  PARITY UNPINNED (the reference ships no tests).
+this package; lt_mapper_b200 never does.  First-party logic is pinned against the reference's own sources compiled
+behind stand-in third-party headers (oracle/ref.py, tests/test_ref_pin.py); PARITY UNPINNED for the restated PCL / FLANN /
+Eigen semantics (the reference ships no tests).
 """
 import ctypes
 import os

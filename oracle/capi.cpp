@@ -1,5 +1,5 @@
 // ORACLE (test infrastructure, not product code): C entry points so that tests/ and bench.py's CPU
-// legs can drive the oracle through ctypes.  See oracle.h for scope.  PARITY UNPINNED.
+// legs can drive the oracle through ctypes.  See oracle.h for scope and for what is / is not pinned.
 #include "oracle.h"
 #include <cstring>
 #include <cstdio>

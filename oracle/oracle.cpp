@@ -1,5 +1,6 @@
 // ORACLE (test infrastructure, not product code) -- see oracle.h for the scope statement.
-// PARITY UNPINNED (no reference tests exist; third-party semantics restated, see comments).
+// First-party logic pinned against the compiled reference sources (oracle/ref_shim, tests/test_ref_pin.py);
+// PARITY UNPINNED for the third-party semantics restated here (no reference tests exist, see comments).
 #include "oracle.h"
 #include <algorithm>
 #include <cfloat>

@@ -1,10 +1,13 @@
 // ORACLE (test infrastructure, not product code).
 // Dependency-free CPU restatement of the LT-removert / LT-map per-keyframe hot path of
-// gisbi-kim/lt-mapper (reference @ 80b6756).  The reference itself cannot be built here (needs
+// gisbi-kim/lt-mapper (reference @ 80b6756).  The reference cannot be linked as shipped (needs
 // ROS, PCL, FLANN, Eigen, OpenCV, Boost: SURVEY.md §8c), so this restatement is the parity
-// definition.  PARITY UNPINNED: the reference has no tests/golden vectors; third-party semantics
-// (PCL transformPointCloud, OctreePointCloudVoxelCentroid, KdTreeFLANN) are restated from their
-// published sources and flagged where used.
+// definition.  PINNING: the reference has no tests/golden vectors.  All FIRST-PARTY logic restated
+// here is pinned bit-for-bit against the reference's own translation units compiled behind
+// third-party stand-in headers (oracle/ref_shim -> oracle/_ref, tests/test_ref_pin.py).
+// PARITY UNPINNED for the third-party semantics (PCL transformPointCloud,
+// OctreePointCloudVoxelCentroid, KdTreeFLANN, Eigen inverse): restated from their published
+// sources and flagged where used; the stand-ins call these same restatements.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // include, link or execute this code.  The product (lt_mapper_b200/) never does.

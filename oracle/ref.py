@@ -30,6 +30,7 @@ def _lib(omp=False):
         L.ref_stage.argtypes = [vp, cp]
         L.ref_pass.argtypes = [vp, ci, ci, ci, f32]
         L.ref_self_removert.argtypes = [vp, ci, ci]
+        L.ref_high_dyn_with_schedule.argtypes = [vp, vp, vp, ci]
         L.ref_param_num.argtypes = [cp, vp, ci]
         L.ref_param_str.argtypes = [cp, cp]
         L.ref_cart2sph.argtypes = [vp, i64, vp]
@@ -163,6 +164,11 @@ class Removerter:
 
     def op(self, name, target=0, source=None, res=0.0):
         _lib(self._omp).ref_pass(self._h, self.OPS[name], target, target if source is None else source, res)
+
+    def high_dyn_with_schedule(self, schedule):
+        """Step 1 with an explicit [(op, res)] schedule (op 0 remove, 1 revert) + the rest of removeHighDynamicPoints."""
+        ops = np.array([s[0] for s in schedule], np.int32); res = np.array([s[1] for s in schedule], np.float32)
+        _lib(self._omp).ref_high_dyn_with_schedule(self._h, ops.ctypes.data, res.ctypes.data, len(ops))
 
     def self_removert(self, sess, repeat):
         _lib(self._omp).ref_self_removert(self._h, sess, repeat)

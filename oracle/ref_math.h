@@ -1,9 +1,11 @@
 // ORACLE (test infrastructure, not product code).
 // CPU restatement of the scalar arithmetic on the LT-removert hot path of gisbi-kim/lt-mapper.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
-// use anything under oracle/.  PARITY UNPINNED: the reference ships no tests or golden vectors
-// (SURVEY.md §4, §8c); this header is pinned instead against this container's libm (atan2f) and
-// against hand-computed known answers in tests/test_oracle_kat.py.
+// use anything under oracle/.  The reference ships no tests or golden vectors.
+// The first-party arithmetic here (cart2sph, rad2deg, pixel index, image size) is pinned bit-for-bit
+// against the reference's own utility.cpp compiled behind stand-in headers (oracle/ref_shim,
+// tests/test_ref_pin.py), against this container's libm (atan2f) and against hand-computed known
+// answers (tests/test_oracle_kat.py).  PARITY UNPINNED for the PCL transform restated at the end.
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // Build with -ffp-contract=off and no -march flag: the reference is a plain x86-64 Release build

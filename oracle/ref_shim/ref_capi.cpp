@@ -217,6 +217,28 @@ int ref_pass(void* h, int op, int target, int source, float res) {
     }
     return 0;
 }
+// Step 1 with an explicit remove / revert schedule (op 0 = removeOnce(res); op 1 = resetCurrrentMapAsDynamic, revertOnce(res),
+// resetCurrrentMapAsStatic -- the building blocks of selfRemovert, Removerter.cpp:1378-1393) applied to each session, followed by the
+// rest of removeHighDynamicPoints (Removerter.cpp:1591-1604).  Every call is one of the reference's own member functions.
+void ref_high_dyn_with_schedule(void* h, const int* ops, const float* res, int n) {
+    Removerter* R = (Removerter*)h;
+    for (int s = 0; s < 2; ++s) {
+        Session& S = sess_of(R, s);
+        for (int i = 0; i < n; ++i) {
+            if (ops[i] == 0) R->removeOnce(S, S, res[i]);
+            else { R->resetCurrrentMapAsDynamic(S); R->revertOnce(S, S, res[i]); R->resetCurrrentMapAsStatic(S); }
+        }
+    }
+    Session& C = R->central_sess_; Session& Q = R->query_sess_;
+    C.extractHighDynPointsViaKnnDiff(C.map_global_curr_static_);
+    Q.extractHighDynPointsViaKnnDiff(Q.map_global_curr_static_);
+    auto mc = mergeScansWithinGlobalCoordUtil(C.keyframe_scans_dynamic_, C.keyframe_poses_, C.kSE3MatExtrinsicLiDARtoPoseBase);
+    auto mq = mergeScansWithinGlobalCoordUtil(Q.keyframe_scans_dynamic_, Q.keyframe_poses_, Q.kSE3MatExtrinsicLiDARtoPoseBase);
+    octreeDownsampling(mc, mc, 0.05);
+    octreeDownsampling(mq, mq, 0.05);
+    pcl::io::savePCDFileBinary(R->save_pcd_directory_ + "central_sess_high_dyn.pcd", *mc);
+    pcl::io::savePCDFileBinary(R->save_pcd_directory_ + "query_sess_high_dyn.pcd", *mq);
+}
 void ref_self_removert(void* h, int sess, int repeat) { Removerter* R = (Removerter*)h; R->selfRemovert(sess_of(R, sess), repeat); }
 
 int64_t ref_scan2rimg(void* h, const float* xyzi, int64_t n, int rows, int cols, float* rimg) {

@@ -288,3 +288,27 @@ def test_keyframe_parsing_matches_the_reference(session_files, small_pair, start
     exp_q = list(removert.parse_keyframes_in_roi(q_poses, central_kf_poses, gap))
     assert R.keyframe_names(1) == [f"{k:06d}.pcd" for k in exp_q]
     R.close()
+
+
+def test_schedule_driven_step1_matches_the_reference(small_pair, scratch):
+    """ref_high_dyn_with_schedule (what bench.py --impl reference times) == the oracle's scheduled Step 1, both sessions."""
+    sched = [(0, 2.5), (0, 2.0), (0, 1.5), (1, 1.0)]
+    R = ref.Removerter(base_params(scratch, num_nn_points_within=1, dist_nn_points_within=0.04), write_files=False)
+    O = oracle.Removerter(schedule=sched, num_knn=1, knn_thr=0.04, threads=4)
+    for s, d in enumerate(small_pair):
+        R.load_session_mem(s, d.xyzi, d.offsets, d.poses)
+        O.load_session(s, d.xyzi, d.offsets, d.poses, np.stack([ref.inverse4x4(p) for p in d.poses]))
+    for st in ("precleaningKeyframes", "makeGlobalMap"):
+        R.stage(st); O.stage(st)
+    R.high_dyn_with_schedule(sched)
+    O.stage("removeHighDynamicPoints")
+    for st in ("parseStaticScansViaProjection", "detectLowDynamicPoints"):
+        R.stage(st); O.stage(st)
+    for s in (0, 1):
+        for name in ("map_global_curr_", "map_global_curr_static_", "map_global_curr_dynamic_", "map_global_nd_strong_", "map_global_nd_weak_",
+                     "map_global_pd_strong_", "map_global_pd_weak_"):
+            assert bits_equal(R.cloud(name, s), O.cloud(name, s)), (name, s)
+        for name in ("keyframe_scans_dynamic_", "keyframe_scans_static_projected_", "scans_knn_diff_"):
+            got, exp = R.scans(name, s), O.clouds(name, s)
+            assert len(got) == len(exp) and all(bits_equal(a, b) for a, b in zip(got, exp)), (name, s)
+    R.close()
