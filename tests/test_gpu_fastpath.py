@@ -101,3 +101,24 @@ def test_fast_path_with_extrinsic_and_order(small_pair):
             g = ctx.cloud_download(ctx.merge_scans_global(ss, ps))
             assert np.array_equal(g.view(np.uint32), merged.view(np.uint32))
     assert exp.sum() > 0
+
+
+@pytest.mark.parametrize("vfov,hfov", [(40.0, 360.0), (33.2, 180.0), (90.0, 360.0), (50.0, 359.0)])
+def test_non_default_fov(small_pair, small_maps, vfov, hfov):
+    """sequence_vfov / sequence_hfov other than 50 x 360 (the oracle side of these is pinned against the compiled reference in
+    tests/test_ref_pin.py): heavy row / column clamping at the narrow settings, every kernel variant."""
+    c = small_pair[0]
+    m = small_maps[0]
+    inv = oracle.inverse_poses(c.poses)
+    exp = {(mode, a): oracle.remove_pass(m, c.xyzi, c.offsets, inv, mode, a, 0.1, vfov=vfov, hfov=hfov)
+           for mode in (oracle.MODE_HD, oracle.MODE_ND, oracle.MODE_PD) for a in (2.5, 0.7)}
+    e_vis, _ = oracle.parse_projected(m, inv[2], 3.0, vfov=vfov, hfov=hfov)
+    for fast, cull in ((False, False), (True, False), (True, True)):
+        with ltr.Context(vfov=vfov, hfov=hfov, fast_path=fast, cull=cull) as ctx:
+            mh = ctx.cloud_upload(m); ss = ctx.scanset_upload(c.xyzi, c.offsets); ps = ctx.poses_upload(c.poses, inv)
+            for (mode, a), e in exp.items():
+                ctx.remove_pass(mh, ss, ps, mode, a)
+                assert np.array_equal(ctx.flags_download(mh), e), (fast, cull, mode, a)
+            pts, off = ctx.scanset_download(ctx.parse_projected(mh, ps, 2, 3, 3.0))
+            assert np.array_equal(pts.view(np.uint32), e_vis.view(np.uint32)), (fast, cull)
+    assert all(e.sum() > 0 for e in exp.values())

@@ -312,3 +312,21 @@ def test_schedule_driven_step1_matches_the_reference(small_pair, scratch):
             got, exp = R.scans(name, s), O.clouds(name, s)
             assert len(got) == len(exp) and all(bits_equal(a, b) for a, b in zip(got, exp)), (name, s)
     R.close()
+
+
+@pytest.mark.parametrize("vfov,hfov", [(40.0, 360.0), (33.2, 180.0), (90.0, 360.0), (50.0, 359.0)])
+def test_non_default_fov_matches_the_reference(small_pair, small_maps, scratch, vfov, hfov):
+    """sequence_vfov / sequence_hfov other than the yaml's 50 x 360: image size, pixel clamping and the HD index set."""
+    c = small_pair[0]
+    m = small_maps[0]
+    R = ref.Removerter(base_params(scratch, sequence_vfov=vfov, sequence_hfov=hfov), write_files=False)
+    R.load_session_mem(0, c.xyzi, c.offsets, c.poses)
+    inv = np.stack([ref.inverse4x4(p) for p in c.poses])
+    for alpha in (2.5, 0.7):
+        rows, cols = oracle.reset_rimg_size(alpha, vfov, hfov)
+        assert (rows, cols) == ref.reset_rimg_size(alpha, vfov, hfov)
+        R.set_cloud("map_global_curr_", m, 0)
+        got = R.dynamic_idx(0, 0, 0, rows, cols, len(m))
+        exp = oracle.remove_pass(m, c.xyzi, c.offsets, inv, oracle.MODE_HD, alpha, 0.1, vfov=vfov, hfov=hfov)
+        assert np.array_equal(got, np.flatnonzero(exp)) and len(got) > 100
+    R.close()
