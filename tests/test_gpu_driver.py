@@ -110,3 +110,55 @@ def test_driver_matches_compiled_reference(tmp_path, small_pair):
     for f in files:
         a, b = removert.read_pcd(str(out_ref / f)), removert.read_pcd(str(out_gpu / f))
         assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), f
+
+
+def test_cascade_through_files_matches_compiled_reference(tmp_path):
+    """Multi-session cascade the way the reference does it: a run's scans_updated/ + the central poses become the next
+    run's central session, diffed against a third session.  Both implementations consume their OWN first-run outputs; the second-run
+    output trees must still be identical (LT-map composition error would compound here)."""
+    import shutil
+    import synth
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libltremovert_ref.so not built")
+    K = 4
+    sessions = [synth.make_session(s, K, beams=32, az_steps=900) for s in (0, 1, 2)]
+    for name, s in zip("abc", sessions):
+        _write_session(tmp_path / name, s)
+    common = dict(sequence_vfov=50.0, sequence_hfov=360.0, keyframe_gap=1, start_idx=0, end_idx=100, downsample_voxel_size=0.05,
+                  num_nn_points_within=2, dist_nn_points_within=0.01)
+    ident = [1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+
+    def run_ref(central_scans, query, out):
+        R = ref.Removerter(dict(common, saveMapPCD=True, save_pcd_directory=str(out), ExtrinsicLiDARtoPoseBase=ident,
+                                central_sess_scan_dir=str(central_scans), central_sess_pose_path=f"{tmp_path}/a/poses.txt",
+                                query_sess_scan_dir=f"{tmp_path}/{query}/Scans/", query_sess_pose_path=f"{tmp_path}/{query}/poses.txt"))
+        R.run()
+        R.close()
+
+    def run_gpu(central_scans, query, out):
+        cfg = tmp_path / f"params_{query}.yaml"
+        cfg.write_text("removert:\n  saveMapPCD: true\n" + f'  save_pcd_directory: "{out}"\n'
+                       + f'  central_sess_scan_dir: "{central_scans}"\n  central_sess_pose_path: "{tmp_path}/a/poses.txt"\n'
+                       + f'  query_sess_scan_dir: "{tmp_path}/{query}/Scans/"\n  query_sess_pose_path: "{tmp_path}/{query}/poses.txt"\n'
+                       + "  ExtrinsicLiDARtoPoseBase: [" + ", ".join(repr(v) for v in ident) + "]\n"
+                       + "".join(f"  {k}: {v}\n" for k, v in common.items()))
+        r = subprocess.run([BIN, "--config", str(cfg)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+
+    for tag, run in (("ref", run_ref), ("gpu", run_gpu)):
+        run(tmp_path / "a" / "Scans", "b", tmp_path / f"{tag}1")
+        nxt = tmp_path / f"{tag}_central2"
+        shutil.copytree(tmp_path / f"{tag}1" / "scans_updated", nxt)
+        run(nxt, "c", tmp_path / f"{tag}2")
+
+    def tree(d):
+        return sorted(os.path.relpath(os.path.join(p, f), d) for p, _, fs in os.walk(d) for f in fs)
+    for stage in ("1", "2"):
+        a, b = tmp_path / ("ref" + stage), tmp_path / ("gpu" + stage)
+        files = tree(a)
+        assert files == tree(b) and len(files) >= 14 + 5 * K
+        for f in files:
+            x, y = removert.read_pcd(str(a / f)), removert.read_pcd(str(b / f))
+            assert x.shape == y.shape and np.array_equal(x.view(np.uint32), y.view(np.uint32)), (stage, f)
+    assert len(removert.read_pcd(str(tmp_path / "gpu2" / "nd_map.pcd"))) > 0 and len(removert.read_pcd(str(tmp_path / "gpu2" / "pd_map.pcd"))) > 0
