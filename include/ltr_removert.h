@@ -77,6 +77,12 @@ int ltrh_run_step3(ltrh_removerter* r);   /* updateCurrentMap .. updateScansScan
 /* Benchmark/test plumbing (not in the reference): restores the state right after Step 0 (map_global_curr_ = the
  * voxelised original map, everything derived freed) so that Step 1+2 can be timed repeatedly; clears log and timings. */
 int ltrh_reset_to_step0(ltrh_removerter* r);
+/* LT-map cascade (multi-session chaining).  The reference has no call for this: it is done by pointing the next run's
+ * central_sess_scan_dir at the previous run's scans_updated/ (written by saveUpdatedScans, Removerter.cpp:1620-1623) with the same
+ * central pose file; Session::loadKeyframes (Session.cpp:272-303) then voxel-grids each scan at downsample_voxel_size.  This
+ * entry does exactly that in memory after ltrh_run_step3: central keyframe_scans_ <- VoxelGrid(keyframe_scans_updated_), central poses
+ * kept, query session and every derived cloud released, log cleared.  Then ltrh_load_session(r, 1, next query) and run the steps again. */
+int ltrh_cascade_promote_updated(ltrh_removerter* r);
 /* a single member function of Removerter by name, e.g. "removeHighDynamicPoints" */
 int ltrh_stage(ltrh_removerter* r, const char* name);
 

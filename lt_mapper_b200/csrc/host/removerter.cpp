@@ -2,6 +2,7 @@
 // Statement order follows ltremovert/src/Removerter.cpp and ltremovert/src/Session.cpp (cited per function);
 // see removerter.h.  No arithmetic on points happens here.
 #include "removerter.h"
+#include "io.h"
 #include <chrono>
 #include <cstring>
 #include <cstdio>
@@ -517,6 +518,50 @@ int Removerter::reset_to_step0() {
     return LTR_OK;
 }
 
+// LT-map cascade.  The reference chains sessions through its file protocol: a run's scans_updated/ directory and the
+// central pose file are handed to the next run as its central session, where Session::loadKeyframes (Session.cpp:272-303) reads
+// each scan back and passes it through pcl::VoxelGrid(downsample_voxel_size).  This does the same in memory: the updated scans
+// (Removerter.cpp:1606-1650, what saveUpdatedScans writes) are brought to the host, voxel-gridded with the same load-time
+// restatement the file driver uses (io.cpp), and become keyframe_scans_ of the central session; its poses stay.  Everything
+// derived from the finished pair, and the query session, is released; the caller loads the next query and runs Steps 0-3 again.
+int Removerter::cascade_promote_updated() {
+    Session& C = central_sess_;
+    if (C.keyframe_scans_updated_ < 0) return fail(LTR_ERR_INVALID, "cascade: Step 3 has not run (no keyframe_scans_updated_)");
+    int32_t K = 0; int64_t total = 0;
+    CK(ltr_scanset_info(ctx, C.keyframe_scans_updated_, &K, &total));
+    std::vector<float> xyzi((size_t)std::max<int64_t>(total, 1) * 4);
+    std::vector<int64_t> off((size_t)K + 1, 0);
+    CK(ltr_scanset_download(ctx, C.keyframe_scans_updated_, xyzi.data(), total, off.data()));
+    std::vector<float> out;
+    std::vector<int64_t> out_off((size_t)K + 1, 0);
+    out.reserve(xyzi.size());
+    for (int k = 0; k < K; ++k) {
+        HostCloud in((size_t)(off[k + 1] - off[k]));
+        for (size_t i = 0; i < in.size(); ++i) {
+            const float* p = &xyzi[(size_t)(off[k] + (int64_t)i) * 4];
+            in[i] = {p[0], p[1], p[2], p[3]};
+        }
+        const HostCloud v = voxel_grid(in, P.downsample_voxel_size, nullptr);
+        for (const auto& p : v) { out.push_back(p.x); out.push_back(p.y); out.push_back(p.z); out.push_back(p.intensity); }
+        out_off[(size_t)k + 1] = (int64_t)(out.size() / 4);
+    }
+    for (Session* s : {&central_sess_, &query_sess_}) {
+        for (auto& kv : s->cloud_names()) if (*kv.second >= 0) { CK(ltr_cloud_free(ctx, *kv.second)); *kv.second = -1; }
+        for (auto& kv : s->scanset_names()) if (*kv.second >= 0) { CK(ltr_scanset_free(ctx, *kv.second)); *kv.second = -1; }
+    }
+    for (auto& kv : saved) CK(ltr_cloud_free(ctx, kv.second));
+    saved.clear();
+    if (query_sess_.keyframe_poses_ >= 0) { CK(ltr_poses_free(ctx, query_sess_.keyframe_poses_)); query_sess_.keyframe_poses_ = -1; }
+    query_sess_.num_keyframes_ = 0;
+    ltr_scanset ss;
+    if (out.empty()) out.resize(4);
+    CK(ltr_scanset_upload(ctx, out.data(), out_off.data(), K, &ss));
+    C.keyframe_scans_ = ss;
+    log.clear();
+    timing.clear();
+    return LTR_OK;
+}
+
 }  // namespace ltremovert_b200
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -578,6 +623,7 @@ int ltrh_run_step0(ltrh_removerter* r) { r->R->err.clear(); return r->R->run_ste
 int ltrh_run_step12(ltrh_removerter* r) { r->R->err.clear(); return r->R->run_step12(); }
 int ltrh_run_step3(ltrh_removerter* r) { r->R->err.clear(); return r->R->run_step3(); }
 int ltrh_reset_to_step0(ltrh_removerter* r) { r->R->err.clear(); return r->R->reset_to_step0(); }
+int ltrh_cascade_promote_updated(ltrh_removerter* r) { if (!r) return LTR_ERR_INVALID; r->R->err.clear(); return r->R->cascade_promote_updated(); }
 
 int ltrh_stage(ltrh_removerter* r, const char* name) {
     Removerter& R = *r->R;

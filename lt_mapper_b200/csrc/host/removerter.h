@@ -66,6 +66,7 @@ public:
     int run_step12();
     int run_step3();
     int reset_to_step0();  // benchmark plumbing, see include/ltr_removert.h
+    int cascade_promote_updated();  // LT-map cascade: keyframe_scans_updated_ -> the next run's central keyframe_scans_ (see .cpp)
 
     // ---- Session methods (Session.cpp) ----
     int parseScansViaProjection(Session& s, ltr_cloud map, ltr_scanset* vec_to_store);     // Session.cpp:348-360

@@ -41,7 +41,7 @@ class Comm(ctypes.Structure):
 
 
 HOST_EXPORTS = ["ltrh_params_default", "ltrh_create", "ltrh_destroy", "ltrh_last_error", "ltrh_set_comm", "ltrh_context",
-                "ltrh_load_session", "ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0", "ltrh_stage", "ltrh_cloud",
+                "ltrh_load_session", "ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0", "ltrh_cascade_promote_updated", "ltrh_stage", "ltrh_cloud",
                 "ltrh_scanset", "ltrh_timing", "ltrh_log_count", "ltrh_log_get", "ltrh_io_last_error", "ltrh_io_read_pcd", "ltrh_io_write_pcd",
                 "ltrh_io_read_poses", "ltrh_io_parse_keyframes", "ltrh_io_parse_keyframes_in_roi", "ltrh_io_voxel_grid", "ltrh_io_yaml_get"]
 
@@ -67,7 +67,7 @@ def host_lib():
     L.ltrh_context.argtypes = [vp]
     L.ltrh_context.restype = vp
     L.ltrh_load_session.argtypes = [vp, i32, vp, vp, vp, vp, i32]
-    for f in ("ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0"):
+    for f in ("ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0", "ltrh_cascade_promote_updated"):
         getattr(L, f).argtypes = [vp]
     L.ltrh_stage.argtypes = [vp, ctypes.c_char_p]
     L.ltrh_cloud.argtypes = [vp, ctypes.c_char_p, i32, P(i32)]
@@ -271,6 +271,10 @@ class Removerter:
 
     def reset_to_step0(self):
         self._ck(host_lib().ltrh_reset_to_step0(self._h))
+
+    def cascade_promote_updated(self):
+        """LT-map cascade: the updated scans become the central session of the next run (ltrh_cascade_promote_updated)."""
+        self._ck(host_lib().ltrh_cascade_promote_updated(self._h))
 
     def stage(self, name):
         self._ck(host_lib().ltrh_stage(self._h, name.encode()))

@@ -79,3 +79,47 @@ def test_selfremovert_schedule(small_pair):
     O, G = _run_both(small_pair, sched, 2, 0.01)
     _compare(O, G)
     G.close()
+
+
+def test_in_memory_cascade(small_pair):
+    """Three-session LT-map cascade through ltrh_cascade_promote_updated == the oracle chained by hand the way the reference's file
+    protocol chains runs (scans_updated -> VoxelGrid at load -> next central session).  The file-level equivalent is checked
+    against the compiled reference in tests/test_gpu_driver.py."""
+    import synth
+    K = 4
+    sess = [synth.make_session(s, K, beams=32, az_steps=900) for s in (0, 1, 2)]
+
+    def grid(d):   # Session::loadKeyframes' pcl::VoxelGrid (Session.cpp:284-289) on every scan
+        sc = [removert.voxel_grid(d.scan(k), 0.05)[0] for k in range(d.K)]
+        return np.concatenate(sc), np.concatenate([[0], np.cumsum([len(a) for a in sc])]).astype(np.int64)
+
+    loaded = [grid(d) for d in sess]
+    inv = [oracle.inverse_poses(d.poses) for d in sess]
+    # oracle, chained by hand
+    O1 = oracle.Removerter(num_knn=2, knn_thr=0.01)
+    O1.load_session(0, *loaded[0], sess[0].poses, inv[0]); O1.load_session(1, *loaded[1], sess[1].poses, inv[1])
+    O1.run(step3=True)
+    upd = [removert.voxel_grid(a, 0.05)[0] for a in O1.clouds("keyframe_scans_updated_", 0)]
+    O2 = oracle.Removerter(num_knn=2, knn_thr=0.01)
+    O2.load_session(0, np.concatenate(upd), np.concatenate([[0], np.cumsum([len(a) for a in upd])]).astype(np.int64), sess[0].poses, inv[0])
+    O2.load_session(1, *loaded[2], sess[2].poses, inv[2])
+    O2.run(step3=True)
+    # device, promoted in place
+    G = removert.Removerter(num_knn=2, knn_thr=0.01)
+    G.load_session(0, *loaded[0], sess[0].poses, inv[0]); G.load_session(1, *loaded[1], sess[1].poses, inv[1])
+    G.run_step0(); G.run_step12(); G.run_step3()
+    _compare(O1, G, step3=True)
+    G.cascade_promote_updated()
+    pts, off = G.scanset("keyframe_scans_", 0)
+    assert all(_same(pts[off[k]:off[k + 1]], upd[k]) for k in range(K))
+    G.load_session(1, *loaded[2], sess[2].poses, inv[2])
+    G.run_step0(); G.run_step12(); G.run_step3()
+    _compare(O2, G, step3=True)
+    assert len(O2.cloud("saved:nd_map")) > 0 and len(O2.cloud("saved:pd_map")) > 0
+    with pytest.raises(Exception):
+        G2 = removert.Removerter()
+        try:
+            G2.cascade_promote_updated()      # Step 3 has not run
+        finally:
+            G2.close()
+    G.close()
