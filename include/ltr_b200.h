@@ -74,6 +74,8 @@ const char* ltr_last_error(const ltr_ctx* ctx);  /* valid until the next call on
 int ltr_synchronize(ltr_ctx* ctx);
 /* number of kernels of this library launched on ctx so far (for bench.py's gpu_launches) */
 int64_t ltr_kernel_launches(const ltr_ctx* ctx);
+/* introspection: how many ltr_voxel_centroid* calls found their input already one point per voxel in octree order and skipped the sort */
+int64_t ltr_voxel_shortcuts(const ltr_ctx* ctx);
 
 /* ---- data movement -------------------------------------------------------------------------- */
 int ltr_cloud_upload(ltr_ctx* ctx, const float* xyzi, int64_t n, ltr_cloud* out);

@@ -30,7 +30,7 @@ class Config(ctypes.Structure):
 
 
 EXPORTS = [
-    "ltr_config_default", "ltr_create", "ltr_destroy", "ltr_last_error", "ltr_synchronize", "ltr_kernel_launches",
+    "ltr_config_default", "ltr_create", "ltr_destroy", "ltr_last_error", "ltr_synchronize", "ltr_kernel_launches", "ltr_voxel_shortcuts",
     "ltr_cloud_upload", "ltr_cloud_size", "ltr_cloud_download", "ltr_cloud_free", "ltr_cloud_copy", "ltr_cloud_concat",
     "ltr_cloud_device_ptrs", "ltr_cloud_alloc", "ltr_scanset_upload", "ltr_scanset_info", "ltr_scanset_download",
     "ltr_scanset_free", "ltr_scanset_concat_per_keyframe", "ltr_scanset_flatten", "ltr_poses_upload", "ltr_poses_free",
@@ -61,6 +61,8 @@ def lib():
     L.ltr_synchronize.argtypes = [vp]
     L.ltr_kernel_launches.argtypes = [vp]
     L.ltr_kernel_launches.restype = i64
+    L.ltr_voxel_shortcuts.argtypes = [vp]
+    L.ltr_voxel_shortcuts.restype = i64
     L.ltr_cloud_upload.argtypes = [vp, vp, i64, P(i32)]
     L.ltr_cloud_alloc.argtypes = [vp, i64, P(i32)]
     L.ltr_cloud_size.argtypes = [vp, i32, P(i64)]
@@ -346,6 +348,9 @@ class Context:
 
     def kernel_launches(self):
         return lib().ltr_kernel_launches(self._h)
+
+    def voxel_shortcuts(self):
+        return lib().ltr_voxel_shortcuts(self._h)
 
     def synchronize(self):
         self._ck(lib().ltr_synchronize(self._h))

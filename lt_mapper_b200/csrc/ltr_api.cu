@@ -312,6 +312,7 @@ int ltr_synchronize(ltr_ctx* ctx) {
 }
 
 int64_t ltr_kernel_launches(const ltr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t ltr_voxel_shortcuts(const ltr_ctx* ctx) { return ctx ? ctx->vox_shortcuts : 0; }
 
 int ltr_cloud_upload(ltr_ctx* ctx, const float* xyzi, int64_t n, ltr_cloud* out) {
     ApiTrace tr__(ctx, "ltr_cloud_upload");

@@ -55,6 +55,7 @@ struct ltr_ctx {
     std::vector<ltr::DevScanSet> scansets;
     std::vector<ltr::DevPoses> poses;
     int64_t launches = 0;
+    int64_t vox_shortcuts = 0;   // voxelisations answered by the already-one-point-per-voxel shortcut (util.cu)
     bool ext_identity = true;     // base2lidar/lidar2base exactly identity -> second transform step is exact and skipped
     double* d_ext = nullptr;      // 24 doubles: base2lidar rows 0..2, lidar2base rows 0..2
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -301,6 +301,23 @@ __global__ void __launch_bounds__(256) vox_centroid_kernel(PtrView c, const uint
     out.x()[o] = fd(sx, fc); out.y()[o] = fd(sy, fc); out.z()[o] = fd(sz, fc); out.i()[o] = fd(si, fc);
 }
 
+// Shortcut for inputs that are already one point per voxel in octree order (typical: the static subset of a voxelised map,
+// re-voxelised at the same leaf by removeOnce, Removerter.cpp:893-896, when the removed points did not move the bounding box).
+// Decided on the keys of THIS call's box, so it needs no provenance: strictly increasing codes <=> the sort is the identity and
+// every run has length one, and the centroid of a single point is (0.0f + p) / 1.0f -- the same two f32 operations as below.
+__global__ void __launch_bounds__(256) vox_unsorted_kernel(const uint64_t* __restrict__ keys, int64_t n, unsigned int* __restrict__ unsorted) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = (i > 0 && i < n) && !(keys[i] > keys[i - 1]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(unsorted, 1u);
+}
+__global__ void __launch_bounds__(256) vox_single_kernel(PtrView c, DevCloud out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    out.x()[i] = fd(fa(0.0f, c.x[i]), 1.0f); out.y()[i] = fd(fa(0.0f, c.y[i]), 1.0f);
+    out.z()[i] = fd(fa(0.0f, c.z[i]), 1.0f); out.i()[i] = fd(fa(0.0f, c.i[i]), 1.0f);
+}
+constexpr int64_t kVoxShortcutMin = 100000;   // below this the whole voxelisation is launch-bound and the extra sync does not pay
+
 // `out` must be allocated with cap >= in.n; sets out->n
 static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out) {
     const int64_t n = v.n;
@@ -326,6 +343,24 @@ static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out)
     const unsigned nb = (unsigned)((n + T - 1) / T);
     vox_key_kernel<<<nb, T, 0, ctx->stream>>>(v, b, keys0, idx0, bad);
     LTR_LAUNCH_CHECK(ctx);
+    if (n >= kVoxShortcutMin) {
+        unsigned int* unsorted = bad + 1;
+        LTR_CUDA(ctx, cudaMemsetAsync(unsorted, 0, sizeof(unsigned int), ctx->stream));
+        vox_unsorted_kernel<<<nb, T, 0, ctx->stream>>>(keys0, n, unsorted);
+        LTR_LAUNCH_CHECK(ctx);
+        unsigned int h[2] = {0, 1};
+        LTR_CUDA(ctx, cudaMemcpyAsync(h, bad, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h[0]) { dev_free(ctx, p); return fail(ctx, LTR_ERR_UNSUPPORTED, "%u points fall outside the octree bounding box (non-finite coordinates?)", h[0]); }
+        if (!h[1]) {
+            vox_single_kernel<<<nb, T, 0, ctx->stream>>>(v, *out);
+            LTR_LAUNCH_CHECK(ctx);
+            dev_free(ctx, p);
+            out->n = n;
+            ctx->vox_shortcuts++;
+            return LTR_OK;
+        }
+    }
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys0, keys1, idx0, idx1, (int)n, 0, 3 * b.depth, ctx->stream);
     void* tmp;

@@ -120,3 +120,27 @@ def test_knn_diff(small_pair, small_maps, ctx, k, thr):
         assert np.array_equal(_bits(cop[coo[kf]:coo[kf + 1]]), _bits(eco)), kf
         assert np.array_equal(_bits(dip[dio[kf]:dio[kf + 1]]), _bits(edi)), kf
         assert 0 < lab.sum() < len(lab)
+
+
+def test_voxel_shortcut_for_one_point_per_voxel_inputs():
+    """A voxelised cloud (>= 100k points), and a subset that keeps its bounding box, re-voxelised at the same leaf: the sort is skipped
+    (ltr_voxel_shortcuts counts it) and the result still equals the oracle's; a subset that moves the box takes the normal path."""
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([rng.uniform(-40, 40, (600000, 3)), rng.uniform(0, 1, (600000, 1))], 1).astype(np.float32)
+    pts[0, :3] = -0.0                                                    # 0.0f + (-0.0f) = +0.0f must survive the shortcut
+    v = oracle.voxel(pts, 0.2)
+    assert len(v) > 150000
+    lo, hi = v[:, :3].argmin(0), v[:, :3].argmax(0)
+    keep = rng.random(len(v)) < 0.8
+    keep[lo] = True; keep[hi] = True                                      # extremes stay -> same box
+    sub_same = v[keep]
+    drop = np.ones(len(v), bool); drop[lo[0]] = False                     # the x-minimum goes -> the box (and the grid) moves
+    sub_moved = v[drop]
+    with ltr.Context() as ctx:
+        for cloud, expect_shortcut in ((pts, 0), (v, 1), (sub_same, 1), (sub_moved, None)):
+            before = ctx.voxel_shortcuts()
+            got = ctx.cloud_download(ctx.voxel_centroid(ctx.cloud_upload(cloud), 0.2))
+            exp = oracle.voxel(cloud, 0.2)
+            assert got.shape == exp.shape and np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+            if expect_shortcut is not None:
+                assert ctx.voxel_shortcuts() - before == expect_shortcut
