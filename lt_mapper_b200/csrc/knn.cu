@@ -187,7 +187,8 @@ static int build_grid(ltr_ctx* ctx, const DevCloud& target, int k, float thr, Gr
         g.dim[d] = (int)std::floor(((double)mx[d] - g.origin[d]) * g.inv_cell) + 2;
         ncell *= (size_t)g.dim[d];
     }
-    void* p;
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);   // handed to the caller (gb->block) only when the grid is complete
     const size_t cs_bytes = (ncell + 1) * sizeof(uint32_t);
     const size_t cs_pad = (cs_bytes + 255) / 256 * 256;
     LTR_TRY(dev_alloc(ctx, &p, 2 * cs_pad + (size_t)target.n * sizeof(float4)));
@@ -203,6 +204,7 @@ static int build_grid(ltr_ctx* ctx, const DevCloud& target, int k, float thr, Gr
     grid_fill_kernel<<<nb, 256, 0, ctx->stream>>>(view(target), g, start, cnt, sorted);
     LTR_LAUNCH_CHECK(ctx);
     gb->g = g; gb->cell_start = start; gb->sorted = sorted; gb->block = p;
+    p = nullptr;   // ownership moves to gb
     return LTR_OK;
 }
 
@@ -231,7 +233,9 @@ int ltr_knn_diff(ltr_ctx* ctx, ltr_scanset scans_h, ltr_poses poses_h, int32_t p
     const DevCloud target = *tp;
     const int64_t n = scans.pts.n;
     GridBuf gb;
+    ScratchGuard g_grid(ctx, &gb.block);
     void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
     uint8_t* label = nullptr;
     float *gx = nullptr, *gy = nullptr, *gz = nullptr;
     if (n > 0) {
@@ -241,7 +245,7 @@ int ltr_knn_diff(ltr_ctx* ctx, ltr_scanset scans_h, ltr_poses poses_h, int32_t p
         knn_scan_label_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(view(scans.pts), scans.d_off, scans.K, poses.d, pose_offset, ctx->d_ext,
             ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, gb.g, gb.cell_start, gb.sorted, k, thr, label, gx, gy, gz);
         LTR_LAUNCH_CHECK(ctx);
-        dev_free(ctx, gb.block);
+        g_grid.release();
         // re-localise in place (every point; partitioning afterwards keeps the arithmetic identical to the reference,
         // which transforms the two partitions separately with the same per-point operations)
         // NOTE: intensity is carried unchanged.
@@ -257,7 +261,6 @@ int ltr_knn_diff(ltr_ctx* ctx, ltr_scanset scans_h, ltr_poses poses_h, int32_t p
         view_set.pts = sc;
         const int rc = split_scanset_by_flag(ctx, view_set, label, out_coexist, out_diff);
         ltr_cloud_free(ctx, scratch);
-        dev_free(ctx, p);
         return rc;
     }
     // empty input: empty outputs with K keyframes
@@ -281,18 +284,19 @@ int ltr_knn_split_cloud(ltr_ctx* ctx, ltr_cloud query_h, ltr_cloud target_h, int
     LTR_TRY(cloud_new(ctx, q.n, out_far));
     if (q.n == 0) return LTR_OK;
     GridBuf gb;
+    ScratchGuard g_grid(ctx, &gb.block);
     LTR_TRY(build_grid(ctx, target, k, thr, &gb));
-    void* p;
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
     LTR_TRY(dev_alloc(ctx, &p, (size_t)q.n));
     knn_cloud_label_kernel<<<(unsigned)((q.n + 127) / 128), 128, 0, ctx->stream>>>(view(q), gb.g, gb.cell_start, gb.sorted, k, thr, (uint8_t*)p);
     LTR_LAUNCH_CHECK(ctx);
-    dev_free(ctx, gb.block);
+    g_grid.release();
     DevCloud o0 = ctx->clouds[*out_near], o1 = ctx->clouds[*out_far];
     int64_t nf = 0;
     LTR_TRY(stable_partition_by_flag(ctx, q, (const uint8_t*)p, &nf, &o0, &o1));
     ctx->clouds[*out_near].n = o0.n;
     ctx->clouds[*out_far].n = o1.n;
-    dev_free(ctx, p);
     return LTR_OK;
 }
 

@@ -122,13 +122,15 @@ int scanset_new(ltr_ctx* ctx, const std::vector<int64_t>& off, ltr_scanset* out)
     DevScanSet s;
     s.K = K; s.h_off = off; s.used = true;
     s.pts.n = off[K]; s.pts.cap = round_cap(off[K]); s.pts.used = true;
-    void* p;
-    LTR_TRY(dev_alloc(ctx, &p, (size_t)s.pts.cap * 4 * sizeof(float)));
-    s.pts.base = (float*)p;
-    LTR_TRY(dev_alloc(ctx, &p, (size_t)(K + 1) * sizeof(int64_t)));
-    s.d_off = (int64_t*)p;
+    void *p_pts = nullptr, *p_off = nullptr;
+    ScratchGuard g_pts(ctx, &p_pts), g_off(ctx, &p_off);   // disarmed once the handle owns both blocks
+    LTR_TRY(dev_alloc(ctx, &p_pts, (size_t)s.pts.cap * 4 * sizeof(float)));
+    s.pts.base = (float*)p_pts;
+    LTR_TRY(dev_alloc(ctx, &p_off, (size_t)(K + 1) * sizeof(int64_t)));
+    s.d_off = (int64_t*)p_off;
     LTR_CUDA(ctx, cudaMemcpyAsync(s.d_off, off.data(), (size_t)(K + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `off` may be a temporary
+    p_pts = nullptr; p_off = nullptr;
     ctx->scansets[slot] = s;
     *out = slot;
     return LTR_OK;
@@ -161,25 +163,27 @@ __global__ void soa_to_aos_kernel(const float* __restrict__ x, const float* __re
 
 static int upload_points(ltr_ctx* ctx, const float* xyzi, DevCloud& c) {
     if (c.n == 0) return LTR_OK;
-    void* stage;
+    void* stage = nullptr;
+    ScratchGuard g_stage(ctx, &stage);
     LTR_TRY(dev_alloc(ctx, &stage, (size_t)c.n * 16));
     LTR_CUDA(ctx, cudaMemcpyAsync(stage, xyzi, (size_t)c.n * 16, cudaMemcpyHostToDevice, ctx->stream));
     const int T = 256;
     aos_to_soa_kernel<<<(unsigned)((c.n + T - 1) / T), T, 0, ctx->stream>>>((const float4*)stage, c.x(), c.y(), c.z(), c.i(), c.n);
     LTR_LAUNCH_CHECK(ctx);
-    dev_free(ctx, stage);
+    g_stage.release();
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // caller's host buffer is only read during the call
     return LTR_OK;
 }
 static int download_points(ltr_ctx* ctx, const DevCloud& c, float* xyzi) {
     if (c.n == 0) return LTR_OK;
-    void* stage;
+    void* stage = nullptr;
+    ScratchGuard g_stage(ctx, &stage);
     LTR_TRY(dev_alloc(ctx, &stage, (size_t)c.n * 16));
     const int T = 256;
     soa_to_aos_kernel<<<(unsigned)((c.n + T - 1) / T), T, 0, ctx->stream>>>(c.x(), c.y(), c.z(), c.i(), (float4*)stage, c.n);
     LTR_LAUNCH_CHECK(ctx);
     LTR_CUDA(ctx, cudaMemcpyAsync(xyzi, stage, (size_t)c.n * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    dev_free(ctx, stage);
+    g_stage.release();
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return LTR_OK;
 }

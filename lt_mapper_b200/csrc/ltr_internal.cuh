@@ -113,6 +113,17 @@ struct ApiTrace {
 // allocation helpers (stream-ordered)
 int dev_alloc(ltr_ctx* ctx, void** p, size_t bytes);
 void dev_free(ltr_ctx* ctx, void* p);
+// Returns a scratch block to the context's cache on every exit path (LTR_TRY / LTR_CUDA return early on errors).
+// Declare it right after the pointer it watches; release() frees now (so the block can be reused by the next allocation).
+struct ScratchGuard {
+    ltr_ctx* ctx;
+    void** pp;
+    ScratchGuard(ltr_ctx* c, void** p) : ctx(c), pp(p) {}
+    ~ScratchGuard() { release(); }
+    void release() { if (*pp) { dev_free(ctx, *pp); *pp = nullptr; } }
+    ScratchGuard(const ScratchGuard&) = delete;
+    ScratchGuard& operator=(const ScratchGuard&) = delete;
+};
 
 int cloud_new(ltr_ctx* ctx, int64_t n, ltr_cloud* out);          // uninitialised cloud of n points
 int cloud_get(ltr_ctx* ctx, ltr_cloud h, DevCloud** c);

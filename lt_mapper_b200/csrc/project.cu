@@ -277,6 +277,7 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     std::memset(&ca, 0, sizeof(ca));
     const bool use_cull = use_fast && cand && ctx->cfg.fast_path >= 2 && B <= 32 && map->n >= kTilePts;
     void *p_tiles = nullptr, *p_pyr = nullptr;
+    ScratchGuard g_tiles(ctx, &p_tiles), g_pyr(ctx, &p_pyr);
     if (use_cull) {
         ca.enabled = 1;
         ca.ntiles = (map->n + kTilePts - 1) / kTilePts;
@@ -297,7 +298,8 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     std::vector<int> launch_units;
     ctx->ev_used = 0;
     if (map->n > 0 && kf_end > kf_begin) {
-        void *p_rimg, *p_win;
+        void *p_rimg = nullptr, *p_win = nullptr;
+        ScratchGuard g_rimg(ctx, &p_rimg), g_win(ctx, &p_win);
         LTR_TRY(dev_alloc(ctx, &p_rimg, (size_t)B * npx * sizeof(uint32_t) * (use_fast ? 2 : 1)));
         LTR_TRY(dev_alloc(ctx, &p_win, (size_t)B * npx * sizeof(uint64_t)));
         uint32_t* rimg = (uint32_t*)p_rimg;
@@ -351,11 +353,9 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
             else resolve_kernel<false><<<rb, 256, 0, ctx->stream>>>(rimg, win, nb * npx, diff_thres, map->flags);
             LTR_LAUNCH_CHECK(ctx);
         }
-        dev_free(ctx, p_rimg);
-        dev_free(ctx, p_win);
     }
-    dev_free(ctx, p_tiles);
-    dev_free(ctx, p_pyr);
+    g_tiles.release();
+    g_pyr.release();
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     if (n_dynamic) LTR_TRY(count_flags(ctx, map->flags, map->n, n_dynamic));
     LTR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
@@ -392,11 +392,13 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
     if (use_fast) LTR_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     void *p_list = nullptr, *p_cnt = nullptr;
+    ScratchGuard g_list(ctx, &p_list), g_cnt(ctx, &p_cnt);
     std::vector<int> launch_units;
     ctx->ev_used = 0;
     if (K > 0 && mapc.n > 0) {
         const int B = std::max(1, std::min(ctx->cfg.keyframe_batch, K));
-        void *p_win, *p_amin = nullptr;
+        void *p_win = nullptr, *p_amin = nullptr;
+        ScratchGuard g_win(ctx, &p_win), g_amin(ctx, &p_amin);
         LTR_TRY(dev_alloc(ctx, &p_win, (size_t)B * npx * sizeof(uint64_t)));
         if (use_fast) LTR_TRY(dev_alloc(ctx, &p_amin, (size_t)B * npx * sizeof(uint32_t)));
         uint32_t* amin = (uint32_t*)p_amin;
@@ -429,8 +431,8 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
             parse_compact_kernel<<<nb, 1024, 0, ctx->stream>>>(win, (int)npx, (uint32_t*)p_list + (size_t)k0 * npx, (unsigned int*)p_cnt + k0);
             LTR_LAUNCH_CHECK(ctx);
         }
-        dev_free(ctx, p_win);
-        dev_free(ctx, p_amin);
+        g_win.release();
+        g_amin.release();
         std::vector<unsigned int> cnt((size_t)K);
         LTR_CUDA(ctx, cudaMemcpyAsync(cnt.data(), p_cnt, (size_t)K * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -443,8 +445,8 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
             (int)npx, ctx->d_ext, ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, os.pts);
         LTR_LAUNCH_CHECK(ctx);
     }
-    dev_free(ctx, p_list);
-    dev_free(ctx, p_cnt);
+    g_list.release();
+    g_cnt.release();
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     LTR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     float ms = 0.0f;
@@ -461,7 +463,8 @@ int ltr_debug_pixel_index(ltr_ctx* ctx, const float* xyz, int64_t n, int32_t row
                           float* az, float* el) {
     if (!ctx || !xyz || n < 0) return fail(ctx, LTR_ERR_INVALID, "bad argument");
     if (n == 0) return LTR_OK;
-    void* p;
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
     const size_t bytes = (size_t)n * (3 + 5) * 4;
     LTR_TRY(dev_alloc(ctx, &p, bytes));
     float* d_xyz = (float*)p;
@@ -480,7 +483,6 @@ int ltr_debug_pixel_index(ltr_ctx* ctx, const float* xyz, int64_t n, int32_t row
     if (az) LTR_CUDA(ctx, cudaMemcpyAsync(az, d_az, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (el) LTR_CUDA(ctx, cudaMemcpyAsync(el, d_el, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, p);
     return LTR_OK;
 }
 
@@ -497,7 +499,8 @@ int ltr_debug_fast_project(ltr_ctx* ctx, const float* xyz, int64_t n, const doub
     for (int i = 0; i < 16; ++i) id[i] = (i % 5 == 0) ? 1.0 : 0.0;
     LTR_TRY(ltr_poses_upload(ctx, id, inv_pose16, 1, &ph));
     const DevPoses pp = ctx->poses[ph];
-    void* p;
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
     LTR_TRY(dev_alloc(ctx, &p, (size_t)n * (3 + 8) * sizeof(float)));
     float* d_xyz = (float*)p;
     float* d_out = d_xyz + 3 * n;
@@ -507,7 +510,7 @@ int ltr_debug_fast_project(ltr_ctx* ctx, const float* xyz, int64_t n, const doub
     LTR_LAUNCH_CHECK(ctx);
     LTR_CUDA(ctx, cudaMemcpyAsync(out8, d_out, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, p);
+    g_p.release();
     return ltr_poses_free(ctx, ph);
 }
 

@@ -118,7 +118,8 @@ int stable_partition_by_flag(ltr_ctx* ctx, const DevCloud& in, const uint8_t* fl
     const int64_t n = in.n;
     if (n == 0) { *n_flagged = 0; out0->n = 0; out1->n = 0; return LTR_OK; }
     const int nb = (int)((n + kPartTile - 1) / kPartTile);
-    void* p;
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
     LTR_TRY(dev_alloc(ctx, &p, (size_t)(2 * nb + 2) * sizeof(uint32_t)));
     uint32_t* cnt = (uint32_t*)p;
     uint32_t* off = cnt + nb;
@@ -131,7 +132,7 @@ int stable_partition_by_flag(ltr_ctx* ctx, const DevCloud& in, const uint8_t* fl
     uint32_t total = 0;
     LTR_CUDA(ctx, cudaMemcpyAsync(&total, off + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, p);
+    g_p.release();
     *n_flagged = total;
     out1->n = total;
     out0->n = n - total;
@@ -141,7 +142,8 @@ int stable_partition_by_flag(ltr_ctx* ctx, const DevCloud& in, const uint8_t* fl
 int count_flags(ltr_ctx* ctx, const uint8_t* flags, int64_t n, int64_t* count) {
     if (n == 0) { *count = 0; return LTR_OK; }
     const int nb = (int)((n + kPartTile - 1) / kPartTile);
-    void* p;
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
     LTR_TRY(dev_alloc(ctx, &p, (size_t)(2 * nb + 2) * sizeof(uint32_t)));
     uint32_t* cnt = (uint32_t*)p;
     part_count_kernel<<<nb, kPartThreads, 0, ctx->stream>>>(flags, n, cnt);
@@ -151,7 +153,7 @@ int count_flags(ltr_ctx* ctx, const uint8_t* flags, int64_t n, int64_t* count) {
     uint32_t total = 0;
     LTR_CUDA(ctx, cudaMemcpyAsync(&total, cnt + 2 * nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, p);
+    g_p.release();
     *count = total;
     return LTR_OK;
 }
@@ -159,11 +161,12 @@ int count_flags(ltr_ctx* ctx, const uint8_t* flags, int64_t n, int64_t* count) {
 int exclusive_scan_u32(ltr_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n) {
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, n, ctx->stream);
-    void* tmp;
+    void* tmp = nullptr;
+    ScratchGuard g_tmp(ctx, &tmp);
     LTR_TRY(dev_alloc(ctx, &tmp, tmp_bytes));
     LTR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, n, ctx->stream));
     ctx->launches += 2;
-    dev_free(ctx, tmp);
+    g_tmp.release();
     return LTR_OK;
 }
 
@@ -193,7 +196,8 @@ __global__ void __launch_bounds__(256) minmax_kernel(PtrView c, uint32_t* __rest
 }
 
 static int minmax_view(ltr_ctx* ctx, const PtrView& v, float mn[3], float mx[3]) {
-    void* p;
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
     LTR_TRY(dev_alloc(ctx, &p, 6 * sizeof(uint32_t)));
     uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     LTR_CUDA(ctx, cudaMemcpyAsync(p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
@@ -203,7 +207,7 @@ static int minmax_view(ltr_ctx* ctx, const PtrView& v, float mn[3], float mx[3])
     uint32_t res[6];
     LTR_CUDA(ctx, cudaMemcpyAsync(res, p, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, p);
+    g_p.release();
     for (int d = 0; d < 3; ++d) { mn[d] = ord2f(res[d]); mx[d] = ord2f(res[3 + d]); }
     return LTR_OK;
 }
@@ -328,7 +332,8 @@ static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out)
     LTR_TRY(minmax_view(ctx, v, mn, mx));
     const VoxBox b = define_box(mn, mx, leaf);
     if (b.depth > 21) return fail(ctx, LTR_ERR_UNSUPPORTED, "octree depth %d > 21 (extent/leaf too large)", b.depth);
-    void* p;
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
     const size_t kb = (size_t)n * sizeof(uint64_t), ib = (size_t)n * sizeof(uint32_t);
     LTR_TRY(dev_alloc(ctx, &p, 2 * kb + 4 * ib + 256));
     uint64_t* keys0 = (uint64_t*)p;
@@ -351,11 +356,11 @@ static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out)
         unsigned int h[2] = {0, 1};
         LTR_CUDA(ctx, cudaMemcpyAsync(h, bad, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (h[0]) { dev_free(ctx, p); return fail(ctx, LTR_ERR_UNSUPPORTED, "%u points fall outside the octree bounding box (non-finite coordinates?)", h[0]); }
+        if (h[0]) { g_p.release(); return fail(ctx, LTR_ERR_UNSUPPORTED, "%u points fall outside the octree bounding box (non-finite coordinates?)", h[0]); }
         if (!h[1]) {
             vox_single_kernel<<<nb, T, 0, ctx->stream>>>(v, *out);
             LTR_LAUNCH_CHECK(ctx);
-            dev_free(ctx, p);
+            g_p.release();
             out->n = n;
             ctx->vox_shortcuts++;
             return LTR_OK;
@@ -363,11 +368,12 @@ static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out)
     }
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys0, keys1, idx0, idx1, (int)n, 0, 3 * b.depth, ctx->stream);
-    void* tmp;
+    void* tmp = nullptr;
+    ScratchGuard g_tmp(ctx, &tmp);
     LTR_TRY(dev_alloc(ctx, &tmp, tmp_bytes));
     LTR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys0, keys1, idx0, idx1, (int)n, 0, 3 * b.depth, ctx->stream));
     ctx->launches += (3 * b.depth + 7) / 8 + 1;
-    dev_free(ctx, tmp);
+    g_tmp.release();
     vox_head_kernel<<<nb, T, 0, ctx->stream>>>(keys1, n, head);
     LTR_LAUNCH_CHECK(ctx);
     LTR_TRY(exclusive_scan_u32(ctx, head, rank, n));
@@ -379,7 +385,7 @@ static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out)
     LTR_CUDA(ctx, cudaMemcpyAsync(&last[1], head + n - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     LTR_CUDA(ctx, cudaMemcpyAsync(&hbad, bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, p);
+    g_p.release();
     if (hbad) return fail(ctx, LTR_ERR_UNSUPPORTED, "%u points fall outside the octree bounding box (non-finite coordinates?)", hbad);
     out->n = (int64_t)last[0] + last[1];
     return LTR_OK;
@@ -427,7 +433,8 @@ __global__ void segment_count_kernel(const uint8_t* __restrict__ flags, const in
 int segment_counts(ltr_ctx* ctx, const uint8_t* flags, const DevScanSet& s, std::vector<int64_t>* counts) {
     counts->assign((size_t)s.K, 0);
     if (s.K == 0) return LTR_OK;
-    void* p;
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
     LTR_TRY(dev_alloc(ctx, &p, (size_t)s.K * sizeof(unsigned long long)));
     LTR_CUDA(ctx, cudaMemsetAsync(p, 0, (size_t)s.K * sizeof(unsigned long long), ctx->stream));
     segment_count_kernel<<<s.K, 256, 0, ctx->stream>>>(flags, s.d_off, s.K, (unsigned long long*)p);
@@ -435,7 +442,7 @@ int segment_counts(ltr_ctx* ctx, const uint8_t* flags, const DevScanSet& s, std:
     std::vector<unsigned long long> h((size_t)s.K);
     LTR_CUDA(ctx, cudaMemcpyAsync(h.data(), p, (size_t)s.K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, p);
+    g_p.release();
     for (int k = 0; k < s.K; ++k) (*counts)[k] = (int64_t)h[k];
     return LTR_OK;
 }
@@ -543,16 +550,15 @@ int ltr_preclean(ltr_ctx* ctx, ltr_scanset scans, float radius, ltr_scanset* out
     DevScanSet* s;
     LTR_TRY(scanset_get(ctx, scans, &s));
     const DevScanSet ss = *s;
-    void* drop;
+    void* drop = nullptr;
+    ScratchGuard g_drop(ctx, &drop);
     LTR_TRY(dev_alloc(ctx, &drop, (size_t)std::max<int64_t>(ss.pts.n, 1)));
     if (ss.pts.n > 0) {
         const int T = 256;
         preclean_flag_kernel<<<(unsigned)((ss.pts.n + T - 1) / T), T, 0, ctx->stream>>>(view(ss.pts), radius, (uint8_t*)drop);
         LTR_LAUNCH_CHECK(ctx);
     }
-    const int rc = split_scanset_by_flag(ctx, ss, (const uint8_t*)drop, out, nullptr);
-    dev_free(ctx, drop);
-    return rc;
+    return split_scanset_by_flag(ctx, ss, (const uint8_t*)drop, out, nullptr);
 }
 
 int ltr_flags_device_ptr(ltr_ctx* ctx, ltr_cloud map, uint8_t** flags, int64_t* n) {
