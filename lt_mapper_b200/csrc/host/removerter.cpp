@@ -532,17 +532,23 @@ int Removerter::cascade_promote_updated() {
     std::vector<float> xyzi((size_t)std::max<int64_t>(total, 1) * 4);
     std::vector<int64_t> off((size_t)K + 1, 0);
     CK(ltr_scanset_download(ctx, C.keyframe_scans_updated_, xyzi.data(), total, off.data()));
-    std::vector<float> out;
-    std::vector<int64_t> out_off((size_t)K + 1, 0);
-    out.reserve(xyzi.size());
+    // host-side load-time VoxelGrid, keyframes are independent (the reference's loadKeyframes loop is serial; the per-scan
+    // arithmetic and its std::sort are unchanged, only different scans run on different threads)
+    std::vector<HostCloud> grids((size_t)K);
+#pragma omp parallel for schedule(dynamic, 1)
     for (int k = 0; k < K; ++k) {
         HostCloud in((size_t)(off[k + 1] - off[k]));
         for (size_t i = 0; i < in.size(); ++i) {
             const float* p = &xyzi[(size_t)(off[k] + (int64_t)i) * 4];
             in[i] = {p[0], p[1], p[2], p[3]};
         }
-        const HostCloud v = voxel_grid(in, P.downsample_voxel_size, nullptr);
-        for (const auto& p : v) { out.push_back(p.x); out.push_back(p.y); out.push_back(p.z); out.push_back(p.intensity); }
+        grids[(size_t)k] = voxel_grid(in, P.downsample_voxel_size, nullptr);
+    }
+    std::vector<float> out;
+    std::vector<int64_t> out_off((size_t)K + 1, 0);
+    out.reserve(xyzi.size());
+    for (int k = 0; k < K; ++k) {
+        for (const auto& p : grids[(size_t)k]) { out.push_back(p.x); out.push_back(p.y); out.push_back(p.z); out.push_back(p.intensity); }
         out_off[(size_t)k + 1] = (int64_t)(out.size() / 4);
     }
     for (Session* s : {&central_sess_, &query_sess_}) {
