@@ -155,6 +155,9 @@ int ltr_knn_split_cloud(ltr_ctx* ctx, ltr_cloud query, ltr_cloud target, int32_t
 /* Evaluates the device restatement of cart2sph + pixel index (utility.cpp:38-56, 118-123) for n points. */
 int ltr_debug_pixel_index(ltr_ctx* ctx, const float* xyz /* n*3 */, int64_t n, int32_t rows, int32_t cols,
                           int32_t* row, int32_t* col, float* range, float* az, float* el);
+/* scan2RangeImg (Removerter.cpp:109-156) of keyframe `kf` exactly as ltr_remove_pass builds it (fast pixel evaluation when the context's
+ * fast_path is on): rows*cols floats, 10000.0f = no point.  Lets tests compare the image itself, not only what is derived from it. */
+int ltr_debug_scan_rimg(ltr_ctx* ctx, ltr_scanset scans, int32_t kf, float res_alpha, float* rimg /* rows*cols */);
 /* Fast-path validation: for n map points and one inverse pose, writes per point 8 floats:
  * fast pre-round column, fast pre-round row, fast range, r/rho | reference pre-round column, row, range, 0;
  * margins4 (optional) = column margin a, column margin b (x r/rho), row margin, relative range margin. */

@@ -36,7 +36,7 @@ EXPORTS = [
     "ltr_scanset_free", "ltr_scanset_concat_per_keyframe", "ltr_scanset_flatten", "ltr_poses_upload", "ltr_poses_free",
     "ltr_preclean", "ltr_merge_scans_global", "ltr_voxel_centroid", "ltr_voxel_centroid_per_keyframe", "ltr_remove_pass",
     "ltr_flags_device_ptr", "ltr_flags_download", "ltr_flags_upload", "ltr_apply_partition", "ltr_parse_projected",
-    "ltr_knn_diff", "ltr_knn_split_cloud", "ltr_debug_pixel_index", "ltr_debug_fast_project", "ltr_reset_rimg_size", "ltr_last_pass_stats", "ltr_profile_get", "ltr_profile_reset", "ltr_timer_start", "ltr_timer_stop", "ltr_trace_dump",
+    "ltr_knn_diff", "ltr_knn_split_cloud", "ltr_debug_pixel_index", "ltr_debug_scan_rimg", "ltr_debug_fast_project", "ltr_reset_rimg_size", "ltr_last_pass_stats", "ltr_profile_get", "ltr_profile_reset", "ltr_timer_start", "ltr_timer_stop", "ltr_trace_dump",
 ]
 
 
@@ -92,6 +92,7 @@ def lib():
     L.ltr_knn_diff.argtypes = [vp, i32, i32, i32, i32, i32, f32, P(i32), P(i32)]
     L.ltr_knn_split_cloud.argtypes = [vp, i32, i32, i32, f32, P(i32), P(i32)]
     L.ltr_debug_pixel_index.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]
+    L.ltr_debug_scan_rimg.argtypes = [vp, i32, i32, ctypes.c_float, vp]
     L.ltr_debug_fast_project.argtypes = [vp, vp, i64, vp, f32, vp, vp]
     L.ltr_reset_rimg_size.argtypes = [f32, f32, f32, P(i32), P(i32)]
     L.ltr_reset_rimg_size.restype = None
@@ -125,6 +126,7 @@ class Context:
         L.ltr_config_default(ctypes.byref(cfg))
         cfg.device = device
         cfg.vfov_deg, cfg.hfov_deg = vfov, hfov
+        self._vfov, self._hfov = vfov, hfov
         if lidar2base is not None:
             l2b = np.ascontiguousarray(lidar2base, np.float64).reshape(16)
             b2l = (np.ascontiguousarray(base2lidar, np.float64).reshape(16) if base2lidar is not None
@@ -313,6 +315,12 @@ class Context:
         self._ck(lib().ltr_debug_pixel_index(self._h, x.ctypes.data, n, rows, cols, row.ctypes.data, col.ctypes.data,
                                              rng.ctypes.data, az.ctypes.data, el.ctypes.data))
         return row, col, rng, az, el
+
+    def debug_scan_rimg(self, scans, kf, res_alpha):
+        rows, cols = reset_rimg_size(res_alpha, self._vfov, self._hfov)
+        out = np.empty((rows, cols), np.float32)
+        self._ck(lib().ltr_debug_scan_rimg(self._h, scans, kf, res_alpha, out.ctypes.data))
+        return out
 
     def debug_fast_project(self, xyz, inv_pose, res_alpha):
         x = _f32(xyz).reshape(-1, 3)

@@ -49,6 +49,32 @@ __global__ void __launch_bounds__(256) scan_rimg_kernel(PtrView scans, const int
     atomicMin(&rimg[(size_t)k * g.rows * g.cols + (size_t)r * g.cols + c], __float_as_uint(s.r));
 }
 
+// The same image through the fast pixel evaluation of project_fast.cuh.  Scan points are already in the sensor frame, so only the
+// angle polynomials are approximate; the column / row are accepted when every value within the margins (the ones validated for the map
+// projection, which additionally cover a transform error that does not exist here) rounds to the same pixel, otherwise -- pixel
+// boundary, point on the z axis -- the reference arithmetic decides.  The range written is always the exact one.
+__global__ void __launch_bounds__(256) scan_rimg_fast_kernel(PtrView scans, const int64_t* __restrict__ off, int kf0, int nb, ImgShape g, FastCfg fc,
+                                                             uint32_t* __restrict__ rimg) {
+    const int64_t begin = off[kf0], end = off[kf0 + nb];
+    const int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    const int k = find_kf_rel(off + kf0, nb, i);
+    const float x = scans.x[i], y = scans.y[i], z = scans.z[i];
+    const FastProj f = fast_sph(x, y, z);
+    int r, c;
+    const bool okc = certain_round(__fmaf_rn(f.az, fc.col_scale, fc.col_off), __fmaf_rn(fc.m_col_b, f.rho_inv_r, fc.m_col_a), g.cols - 1, &c);
+    const bool okr = certain_round(__fmaf_rn(-f.el, fc.row_scale, fc.row_off), fc.m_row, g.rows - 1, &r);
+    float range;
+    if (okc & okr) {
+        range = __fsqrt_rn(fa(fa(fm(x, x), fm(y, y)), fm(z, z)));   // cart2sph's r (utility.cpp:48)
+    } else {
+        const Sph s = cart2sph(x, y, z);
+        pixel_index(s, g, &r, &c);
+        range = s.r;
+    }
+    atomicMin(&rimg[(size_t)k * g.rows * g.cols + (size_t)r * g.cols + c], __float_as_uint(range));
+}
+
 // Exact projection of every map point into every keyframe of the batch.
 //   kCandidatesOnly = true  (HD / revert / PD, diff = scan - map): by monotonicity of f32 subtraction the set
 //       {points with scan - range > thres} is a prefix in range order of the pixel's points, so the pixel winner among
@@ -319,7 +345,8 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
 
             const int64_t npts = scans->h_off[k0 + nb] - scans->h_off[k0];
             if (npts > 0) {
-                scan_rimg_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, k0, nb, g, rimg);
+                if (use_fast) scan_rimg_fast_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, k0, nb, g, fc, rimg);
+                else scan_rimg_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, k0, nb, g, rimg);
                 LTR_LAUNCH_CHECK(ctx);
             }
             if (use_cull) {
@@ -482,6 +509,34 @@ int ltr_debug_pixel_index(ltr_ctx* ctx, const float* xyz, int64_t n, int32_t row
     if (range) LTR_CUDA(ctx, cudaMemcpyAsync(range, d_rng, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (az) LTR_CUDA(ctx, cudaMemcpyAsync(az, d_az, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (el) LTR_CUDA(ctx, cudaMemcpyAsync(el, d_el, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LTR_OK;
+}
+
+int ltr_debug_scan_rimg(ltr_ctx* ctx, ltr_scanset scans_h, int32_t kf, float res_alpha, float* out) {
+    if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    DevScanSet* scans;
+    LTR_TRY(scanset_get(ctx, scans_h, &scans));
+    if (kf < 0 || kf >= scans->K) return fail(ctx, LTR_ERR_INVALID, "keyframe %d outside [0,%d)", kf, scans->K);
+    int32_t rows, cols;
+    ltr_reset_rimg_size(ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, res_alpha, &rows, &cols);
+    if (rows < 1 || cols < 1) return fail(ctx, LTR_ERR_INVALID, "range image %dx%d is empty", rows, cols);
+    const ImgShape g{rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg};
+    const int64_t npx = (int64_t)rows * cols;
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
+    LTR_TRY(dev_alloc(ctx, &p, (size_t)npx * sizeof(uint32_t)));
+    fill_u32_kernel<<<grid_for(npx, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>((uint32_t*)p, kNoPointBits, npx);
+    LTR_LAUNCH_CHECK(ctx);
+    const int64_t npts = scans->h_off[kf + 1] - scans->h_off[kf];
+    if (npts > 0) {
+        if (ctx->cfg.fast_path && npx <= (1 << 18))
+            scan_rimg_fast_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, kf, 1, g,
+                make_fast_cfg(rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, 0), (uint32_t*)p);
+        else scan_rimg_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, kf, 1, g, (uint32_t*)p);
+        LTR_LAUNCH_CHECK(ctx);
+    }
+    LTR_CUDA(ctx, cudaMemcpyAsync(out, p, (size_t)npx * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return LTR_OK;
 }

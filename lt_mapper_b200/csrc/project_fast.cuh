@@ -72,12 +72,8 @@ LTR_DEV float fast_atan01(float a) {
 
 struct FastProj { float az, el, r, rho_inv_r; };  // rho_inv_r = r / rho
 
-// kf: A[0..8], c_hi[9..11], t_lo[12..14] = A * c_lo, ok[15]:  q ~= A * (p - c_hi) - t_lo
-LTR_DEV FastProj fast_project(const float* __restrict__ kf, float x, float y, float z) {
-    const float dx = __fsub_rn(x, kf[9]), dy = __fsub_rn(y, kf[10]), dz = __fsub_rn(z, kf[11]);
-    const float qx = __fmaf_rn(kf[2], dz, __fmaf_rn(kf[1], dy, __fmaf_rn(kf[0], dx, -kf[12])));
-    const float qy = __fmaf_rn(kf[5], dz, __fmaf_rn(kf[4], dy, __fmaf_rn(kf[3], dx, -kf[13])));
-    const float qz = __fmaf_rn(kf[8], dz, __fmaf_rn(kf[7], dy, __fmaf_rn(kf[6], dx, -kf[14])));
+// approximate cart2sph of a point in the sensor frame
+LTR_DEV FastProj fast_sph(float qx, float qy, float qz) {
     const float rho2 = __fmaf_rn(qy, qy, __fmul_rn(qx, qx));
     const float r2 = __fmaf_rn(qz, qz, rho2);
     const float irho = mufu_rsq(rho2), ir = mufu_rsq(r2);
@@ -101,6 +97,15 @@ LTR_DEV FastProj fast_project(const float* __restrict__ kf, float x, float y, fl
         o.el = copysignf(t, qz);
     }
     return o;
+}
+
+// kf: A[0..8], c_hi[9..11], t_lo[12..14] = A * c_lo, ok[15]:  q ~= A * (p - c_hi) - t_lo
+LTR_DEV FastProj fast_project(const float* __restrict__ kf, float x, float y, float z) {
+    const float dx = __fsub_rn(x, kf[9]), dy = __fsub_rn(y, kf[10]), dz = __fsub_rn(z, kf[11]);
+    const float qx = __fmaf_rn(kf[2], dz, __fmaf_rn(kf[1], dy, __fmaf_rn(kf[0], dx, -kf[12])));
+    const float qy = __fmaf_rn(kf[5], dz, __fmaf_rn(kf[4], dy, __fmaf_rn(kf[3], dx, -kf[13])));
+    const float qz = __fmaf_rn(kf[8], dz, __fmaf_rn(kf[7], dy, __fmaf_rn(kf[6], dx, -kf[14])));
+    return fast_sph(qx, qy, qz);
 }
 
 // Rounds a pre-round pixel coordinate when that is certain: returns true and the clamped index iff every value within

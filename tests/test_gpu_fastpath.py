@@ -122,3 +122,23 @@ def test_non_default_fov(small_pair, small_maps, vfov, hfov):
             pts, off = ctx.scanset_download(ctx.parse_projected(mh, ps, 2, 3, 3.0))
             assert np.array_equal(pts.view(np.uint32), e_vis.view(np.uint32)), (fast, cull)
     assert all(e.sum() > 0 for e in exp.values())
+
+
+@pytest.mark.parametrize("vfov,hfov", [(50.0, 360.0), (33.2, 180.0)])
+def test_scan_range_image_fast_equals_exact(small_pair, vfov, hfov):
+    """The scan range image itself (Removerter.cpp:109-156), fast pixel evaluation on and off, against the oracle (whose scan2RangeImg
+    is pinned against the compiled reference): identical bits, at coarse and fine resolutions, with range ties and degenerate points."""
+    c = small_pair[0]
+    rng = np.random.default_rng(11)
+    extra = np.array([[0, 0, 1, 0], [0, 0, -2, 0], [0, 0, 0, 0], [-5, 0.0, 0.3, 0], [-5, -0.0, 0.3, 0], [1e-20, 1e-20, 1e-20, 0], [3, 4, 0, 0], [3, 4, 0, 1]], np.float32)
+    xyzi = np.concatenate([c.xyzi, c.scan(1)[::-1], rng.normal(0, 20, (50000, 4)).astype(np.float32), extra])
+    off = np.array([0, c.offsets[3], len(xyzi)], np.int64)          # two ragged "keyframes"
+    for fast in (False, True):
+        with ltr.Context(vfov=vfov, hfov=hfov, fast_path=fast) as ctx:
+            ss = ctx.scanset_upload(xyzi, off)
+            for alpha in (0.5, 1.0, 2.5, 3.0):
+                rows, cols = oracle.reset_rimg_size(alpha, vfov, hfov)
+                for k in (0, 1):
+                    exp = oracle.scan2rimg(xyzi[off[k]:off[k + 1]], rows, cols, vfov, hfov)
+                    got = ctx.debug_scan_rimg(ss, k, alpha)
+                    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (fast, alpha, k)
