@@ -265,18 +265,36 @@ __device__ __forceinline__ uint64_t spread3(uint32_t v) {  // 21 bits -> every t
     return x;
 }
 
-__global__ void __launch_bounds__(256) vox_key_kernel(PtrView c, VoxBox b, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx,
-                                                      unsigned int* __restrict__ bad) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+__device__ __forceinline__ uint64_t vox_code(const PtrView& c, const VoxBox& b, int64_t i, bool* inside) {
     const double fx = __ddiv_rn(__dsub_rn((double)c.x[i], b.min[0]), b.res);
     const double fy = __ddiv_rn(__dsub_rn((double)c.y[i], b.min[1]), b.res);
     const double fz = __ddiv_rn(__dsub_rn((double)c.z[i], b.min[2]), b.res);
     const double lim = (double)(1u << b.depth);
-    if (!(fx >= 0.0 && fy >= 0.0 && fz >= 0.0 && fx < lim && fy < lim && fz < lim)) atomicAdd(bad, 1u);
+    *inside = fx >= 0.0 && fy >= 0.0 && fz >= 0.0 && fx < lim && fy < lim && fz < lim;
     const uint32_t kx = (uint32_t)__double2uint_rz(fx), ky = (uint32_t)__double2uint_rz(fy), kz = (uint32_t)__double2uint_rz(fz);
-    keys[i] = (spread3(kx) << 2) | (spread3(ky) << 1) | spread3(kz);
-    idx[i] = (uint32_t)i;
+    return (spread3(kx) << 2) | (spread3(ky) << 1) | spread3(kz);
+}
+
+// Also reports (unsorted != nullptr) whether the codes are NOT strictly increasing in input order, for the shortcut below: each
+// thread compares with its predecessor's code, taken from the neighbouring lane (the first lane of a warp recomputes it).
+__global__ void __launch_bounds__(256) vox_key_kernel(PtrView c, VoxBox b, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx,
+                                                      unsigned int* __restrict__ bad, unsigned int* __restrict__ unsorted) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < c.n;
+    uint64_t key = 0;
+    if (live) {
+        bool inside;
+        key = vox_code(c, b, i, &inside);
+        if (!inside) atomicAdd(bad, 1u);
+        keys[i] = key;
+        idx[i] = (uint32_t)i;
+    }
+    if (unsorted) {
+        uint64_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+        if ((threadIdx.x & 31) == 0 && live && i > 0) { bool inside; prev = vox_code(c, b, i - 1, &inside); }
+        const bool out_of_order = live && i > 0 && !(key > prev);
+        if (__any_sync(0xffffffffu, out_of_order) && (threadIdx.x & 31) == 0) atomicOr(unsorted, 1u);
+    }
 }
 
 __global__ void __launch_bounds__(256) vox_head_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ head) {
@@ -309,11 +327,6 @@ __global__ void __launch_bounds__(256) vox_centroid_kernel(PtrView c, const uint
 // re-voxelised at the same leaf by removeOnce, Removerter.cpp:893-896, when the removed points did not move the bounding box).
 // Decided on the keys of THIS call's box, so it needs no provenance: strictly increasing codes <=> the sort is the identity and
 // every run has length one, and the centroid of a single point is (0.0f + p) / 1.0f -- the same two f32 operations as below.
-__global__ void __launch_bounds__(256) vox_unsorted_kernel(const uint64_t* __restrict__ keys, int64_t n, unsigned int* __restrict__ unsorted) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool bad = (i > 0 && i < n) && !(keys[i] > keys[i - 1]);
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(unsorted, 1u);
-}
 __global__ void __launch_bounds__(256) vox_single_kernel(PtrView c, DevCloud out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
@@ -346,13 +359,11 @@ static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out)
     LTR_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(unsigned int), ctx->stream));
     const int T = 256;
     const unsigned nb = (unsigned)((n + T - 1) / T);
-    vox_key_kernel<<<nb, T, 0, ctx->stream>>>(v, b, keys0, idx0, bad);
+    const bool try_shortcut = n >= kVoxShortcutMin;
+    LTR_CUDA(ctx, cudaMemsetAsync(bad + 1, 0, sizeof(unsigned int), ctx->stream));
+    vox_key_kernel<<<nb, T, 0, ctx->stream>>>(v, b, keys0, idx0, bad, try_shortcut ? bad + 1 : nullptr);
     LTR_LAUNCH_CHECK(ctx);
-    if (n >= kVoxShortcutMin) {
-        unsigned int* unsorted = bad + 1;
-        LTR_CUDA(ctx, cudaMemsetAsync(unsorted, 0, sizeof(unsigned int), ctx->stream));
-        vox_unsorted_kernel<<<nb, T, 0, ctx->stream>>>(keys0, n, unsorted);
-        LTR_LAUNCH_CHECK(ctx);
+    if (try_shortcut) {
         unsigned int h[2] = {0, 1};
         LTR_CUDA(ctx, cudaMemcpyAsync(h, bad, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
