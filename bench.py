@@ -108,17 +108,21 @@ def gen_block(rank, kf):
 
 
 class _QuietStdout:
-    """The reference narrates on std::cout (Session.cpp:575); keep bench.py's stdout to the one JSON line."""
+    """Keeps bench.py's stdout to the one JSON line: native code that narrates on fd 1 (the reference on std::cout, Session.cpp:575;
+    NCCL's version banner) is sent to /dev/null or, with to_stderr, to fd 2 for the duration."""
+
+    def __init__(self, to_stderr=False):
+        self._to_stderr = to_stderr
 
     def __enter__(self):
         sys.stdout.flush()
         self._saved = os.dup(1)
-        self._null = os.open(os.devnull, os.O_WRONLY)
-        os.dup2(self._null, 1)
+        self._dst = os.dup(2) if self._to_stderr else os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._dst, 1)
 
     def __exit__(self, *a):
         os.dup2(self._saved, 1)
-        os.close(self._saved); os.close(self._null)
+        os.close(self._saved); os.close(self._dst)
 
 
 def cpu_baseline_run(steps=1, warmup=0):
@@ -218,7 +222,10 @@ def main():
     torch.cuda.set_device(local_rank)
     comm = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with _QuietStdout(to_stderr=True):     # NCCL prints its version banner on stdout at communicator creation
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
         comm = removert.TorchDistComm()
 
     def barrier():
