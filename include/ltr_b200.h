@@ -76,6 +76,9 @@ int ltr_synchronize(ltr_ctx* ctx);
 int64_t ltr_kernel_launches(const ltr_ctx* ctx);
 /* introspection: how many ltr_voxel_centroid* calls found their input already one point per voxel in octree order and skipped the sort */
 int64_t ltr_voxel_shortcuts(const ltr_ctx* ctx);
+/* introspection: bytes of device memory currently handed out by the context's caching allocator (clouds, scan sets, poses and scratch),
+ * bytes parked in its cache, and the high-water mark of the former.  stats3 = { live, cached, peak_live }. */
+int ltr_memory_stats(const ltr_ctx* ctx, int64_t* stats3);
 
 /* ---- data movement -------------------------------------------------------------------------- */
 int ltr_cloud_upload(ltr_ctx* ctx, const float* xyzi, int64_t n, ltr_cloud* out);

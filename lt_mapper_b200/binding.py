@@ -30,7 +30,7 @@ class Config(ctypes.Structure):
 
 
 EXPORTS = [
-    "ltr_config_default", "ltr_create", "ltr_destroy", "ltr_last_error", "ltr_synchronize", "ltr_kernel_launches", "ltr_voxel_shortcuts",
+    "ltr_config_default", "ltr_create", "ltr_destroy", "ltr_last_error", "ltr_synchronize", "ltr_kernel_launches", "ltr_voxel_shortcuts", "ltr_memory_stats",
     "ltr_cloud_upload", "ltr_cloud_size", "ltr_cloud_download", "ltr_cloud_free", "ltr_cloud_copy", "ltr_cloud_concat",
     "ltr_cloud_device_ptrs", "ltr_cloud_alloc", "ltr_scanset_upload", "ltr_scanset_info", "ltr_scanset_download",
     "ltr_scanset_free", "ltr_scanset_concat_per_keyframe", "ltr_scanset_flatten", "ltr_poses_upload", "ltr_poses_free",
@@ -63,6 +63,7 @@ def lib():
     L.ltr_kernel_launches.restype = i64
     L.ltr_voxel_shortcuts.argtypes = [vp]
     L.ltr_voxel_shortcuts.restype = i64
+    L.ltr_memory_stats.argtypes = [vp, vp]
     L.ltr_cloud_upload.argtypes = [vp, vp, i64, P(i32)]
     L.ltr_cloud_alloc.argtypes = [vp, i64, P(i32)]
     L.ltr_cloud_size.argtypes = [vp, i32, P(i64)]
@@ -359,6 +360,12 @@ class Context:
 
     def voxel_shortcuts(self):
         return lib().ltr_voxel_shortcuts(self._h)
+
+    def memory_stats(self):
+        """(live, cached, peak_live) bytes of the context's caching allocator."""
+        s = np.zeros(3, np.int64)
+        self._ck(lib().ltr_memory_stats(self._h, s.ctypes.data))
+        return tuple(int(v) for v in s)
 
     def synchronize(self):
         self._ck(lib().ltr_synchronize(self._h))

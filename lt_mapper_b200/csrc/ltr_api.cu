@@ -317,6 +317,11 @@ int ltr_synchronize(ltr_ctx* ctx) {
 
 int64_t ltr_kernel_launches(const ltr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int64_t ltr_voxel_shortcuts(const ltr_ctx* ctx) { return ctx ? ctx->vox_shortcuts : 0; }
+int ltr_memory_stats(const ltr_ctx* ctx, int64_t* stats3) {
+    if (!ctx || !stats3) return LTR_ERR_INVALID;
+    stats3[0] = (int64_t)ctx->live_bytes; stats3[1] = (int64_t)ctx->cached_bytes; stats3[2] = (int64_t)ctx->peak_live_bytes;
+    return LTR_OK;
+}
 
 int ltr_cloud_upload(ltr_ctx* ctx, const float* xyzi, int64_t n, ltr_cloud* out) {
     ApiTrace tr__(ctx, "ltr_cloud_upload");

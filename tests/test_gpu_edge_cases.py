@@ -122,3 +122,29 @@ def test_degenerate_geometry_goes_through_the_exact_path(ctx):
     ep, _ = oracle.parse_projected(m, I4[0], 3.0)
     assert np.array_equal(pts.view(np.uint32), ep.view(np.uint32))
     assert exp.sum() > 0
+
+
+def test_error_paths_release_their_scratch_memory(ctx):
+    """Calls that fail half-way (non-finite coordinates in the voxeliser, kNN against too few points, bad arguments to a pass) and
+    calls that succeed leave the allocator's live byte count exactly where the handles they created account for it."""
+    good = np.random.default_rng(0).uniform(-5, 5, (200000, 4)).astype(np.float32)
+    bad = good.copy(); bad[1234, 1] = np.nan
+    hg, hb = ctx.cloud_upload(good), ctx.cloud_upload(bad)
+    ss = ctx.scanset_upload(good[:1000], [0, 400, 1000])
+    ps = ctx.poses_upload(np.stack([I4, I4]), np.stack([I4, I4]))
+    tiny = ctx.cloud_upload(good[:1])
+    base = ctx.memory_stats()[0]
+    for _ in range(3):
+        with pytest.raises(ltr.LtrError):
+            ctx.voxel_centroid(hb, 0.1)                       # fails after the output cloud, keys and scratch were allocated
+        with pytest.raises(ltr.LtrError):
+            ctx.knn_diff(ss, ps, tiny, 2, 0.01)
+        with pytest.raises(ltr.LtrError):
+            ctx.remove_pass(hg, ss, ps, 7, 2.5)                # unknown mode
+        assert ctx.memory_stats()[0] == base
+    ctx.remove_pass(hg, ss, ps, ltr.MODE_HD, 2.5)              # first pass on hg allocates its flag array (stays with the handle)
+    ctx.cloud_free(ctx.voxel_centroid(hg, 0.1))
+    before = ctx.memory_stats()[0]
+    ctx.remove_pass(hg, ss, ps, ltr.MODE_HD, 2.5)
+    ctx.cloud_free(ctx.voxel_centroid(hg, 0.1))
+    assert ctx.memory_stats()[0] == before                     # steady state: scratch goes back to the cache
