@@ -130,23 +130,49 @@ __global__ void __launch_bounds__(256) resolve_kernel(const uint32_t* __restrict
     }
 }
 
-// parseProjectedPoints (utility.cpp:80-87): row-major scan of the index image, skipping index 0; one block per keyframe.
-__global__ void __launch_bounds__(1024) parse_compact_kernel(uint64_t* __restrict__ win, int npx, uint32_t* __restrict__ list,
-                                                             unsigned int* __restrict__ count) {
+// parseProjectedPoints (utility.cpp:80-87): row-major scan of the index image, skipping index 0.  Each keyframe's image is cut
+// into chunks of kParseChunk pixels, one block per (chunk, keyframe): a count kernel, then a scatter kernel that starts at the sum of
+// the preceding chunks' counts and compacts its chunk in pixel order (and resets the winner image for the next batch).
+constexpr int kParseChunk = 8192;
+
+__global__ void __launch_bounds__(1024) parse_count_kernel(const uint64_t* __restrict__ win, int npx, int nchunk, unsigned int* __restrict__ chunk_cnt) {
+    __shared__ int s_warp[32];
+    const int k = blockIdx.y, c = blockIdx.x;
+    const uint64_t* w = win + (size_t)k * npx;
+    const int p1 = min((c + 1) * kParseChunk, npx);
+    int n = 0;
+    for (int p = c * kParseChunk + threadIdx.x; p < p1; p += blockDim.x) n += ((uint32_t)w[p] != 0u) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        n = s_warp[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+        if (threadIdx.x == 0) chunk_cnt[(size_t)k * nchunk + c] = (unsigned int)n;
+    }
+}
+
+__global__ void __launch_bounds__(1024) parse_compact_kernel(uint64_t* __restrict__ win, int npx, int nchunk, const unsigned int* __restrict__ chunk_cnt,
+                                                             uint32_t* __restrict__ list, unsigned int* __restrict__ count) {
     __shared__ int s_warp[33];
     __shared__ int s_base;
-    const int k = blockIdx.x;
+    const int k = blockIdx.y, c = blockIdx.x;
     uint64_t* w = win + (size_t)k * npx;
     uint32_t* out = list + (size_t)k * npx;
-    if (threadIdx.x == 0) s_base = 0;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {   // where this chunk's output starts: the counts of the chunks before it
+        int b = 0;
+        for (int j = (int)lane; j < c; j += 32) b += (int)chunk_cnt[(size_t)k * nchunk + j];
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_down_sync(0xffffffffu, b, o);
+        if (lane == 0) s_base = b;
+    }
     __syncthreads();
-    for (int p0 = 0; p0 < npx; p0 += blockDim.x) {
+    const int p1 = min((c + 1) * kParseChunk, npx);
+    for (int p0 = c * kParseChunk; p0 < p1; p0 += blockDim.x) {
         const int p = p0 + threadIdx.x;
         uint32_t idx = 0;
-        if (p < npx) { const uint64_t v = w[p]; idx = (uint32_t)v; if (v != kWinEmpty) w[p] = kWinEmpty; }
+        if (p < p1) { const uint64_t v = w[p]; idx = (uint32_t)v; if (v != kWinEmpty) w[p] = kWinEmpty; }
         const bool keep = idx != 0;
-        // block rank
-        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const unsigned b = __ballot_sync(0xffffffffu, keep);
         const int wrank = __popc(b & ((1u << lane) - 1u));
         if (lane == 0) s_warp[warp] = __popc(b);
@@ -164,7 +190,7 @@ __global__ void __launch_bounds__(1024) parse_compact_kernel(uint64_t* __restric
         if (threadIdx.x == 0) s_base += s_warp[32];
         __syncthreads();
     }
-    if (threadIdx.x == 0) count[k] = (unsigned int)s_base;
+    if (c == nchunk - 1 && threadIdx.x == 0) count[k] = (unsigned int)s_base;
 }
 
 // emits map_local[ptidx] for every listed index: exact two-step transform of the winning map point
@@ -430,7 +456,9 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
         if (use_fast) LTR_TRY(dev_alloc(ctx, &p_amin, (size_t)B * npx * sizeof(uint32_t)));
         uint32_t* amin = (uint32_t*)p_amin;
         LTR_TRY(dev_alloc(ctx, &p_list, (size_t)K * npx * sizeof(uint32_t)));
-        LTR_TRY(dev_alloc(ctx, &p_cnt, (size_t)K * sizeof(unsigned int)));
+        const int nchunk = (int)((npx + kParseChunk - 1) / kParseChunk);
+        LTR_TRY(dev_alloc(ctx, &p_cnt, ((size_t)K + (size_t)B * nchunk) * sizeof(unsigned int)));
+        unsigned int* chunk_cnt = (unsigned int*)p_cnt + K;
         uint64_t* win = (uint64_t*)p_win;
         fill_u64_kernel<<<grid_for(B * npx, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(win, kWinEmpty, B * npx);
         LTR_LAUNCH_CHECK(ctx);
@@ -455,7 +483,10 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
             }
             prof_end(ctx);
             LTR_LAUNCH_CHECK(ctx);
-            parse_compact_kernel<<<nb, 1024, 0, ctx->stream>>>(win, (int)npx, (uint32_t*)p_list + (size_t)k0 * npx, (unsigned int*)p_cnt + k0);
+            parse_count_kernel<<<dim3((unsigned)nchunk, (unsigned)nb), 1024, 0, ctx->stream>>>(win, (int)npx, nchunk, chunk_cnt);
+            LTR_LAUNCH_CHECK(ctx);
+            parse_compact_kernel<<<dim3((unsigned)nchunk, (unsigned)nb), 1024, 0, ctx->stream>>>(win, (int)npx, nchunk, chunk_cnt, (uint32_t*)p_list + (size_t)k0 * npx,
+                                                                                              (unsigned int*)p_cnt + k0);
             LTR_LAUNCH_CHECK(ctx);
         }
         g_win.release();
