@@ -330,3 +330,26 @@ def test_non_default_fov_matches_the_reference(small_pair, small_maps, scratch, 
         exp = oracle.remove_pass(m, c.xyzi, c.offsets, inv, oracle.MODE_HD, alpha, 0.1, vfov=vfov, hfov=hfov)
         assert np.array_equal(got, np.flatnonzero(exp)) and len(got) > 100
     R.close()
+
+
+@pytest.mark.parametrize("seed,beams,az", [(99, 16, 1200), (2024, 48, 600)])
+def test_full_run_on_other_scenes_matches_the_reference(scratch, seed, beams, az):
+    """Removerter::run() end to end (in-memory load, Steps 0-3) on differently seeded / shaped synthetic scenes."""
+    import synth
+    pair = synth.make_pair(5, beams=beams, az_steps=az, seed=seed)
+    R = ref.Removerter(base_params(scratch), write_files=False)
+    O = oracle.Removerter(num_knn=2, knn_thr=0.01, threads=4)
+    for s, d in enumerate(pair):
+        R.load_session_mem(s, d.xyzi, d.offsets, d.poses)
+        O.load_session(s, d.xyzi, d.offsets, d.poses, np.stack([ref.inverse4x4(p) for p in d.poses]))
+    for st in CLOUDS_AFTER:
+        R.stage(st); O.stage(st)
+    for name in ("map_global_curr_static_", "map_global_curr_dynamic_", "map_global_nd_strong_", "map_global_nd_weak_", "map_global_pd_strong_",
+                 "map_global_pd_weak_", "map_global_updated_", "map_global_updated_strong_"):
+        for s in (0, 1):
+            assert bits_equal(R.cloud(name, s), O.cloud(name, s)), (name, s)
+    for name in ("keyframe_scans_updated_", "keyframe_scans_pd_", "keyframe_scans_strong_nd_"):
+        got, exp = R.scans(name, 0), O.clouds(name, 0)
+        assert len(got) == len(exp) == 5 and all(bits_equal(a, b) for a, b in zip(got, exp)), name
+    assert len(R.cloud("map_global_curr_dynamic_", 0)) > 0
+    R.close()
