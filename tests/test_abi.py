@@ -70,3 +70,16 @@ def test_params_defaults_match_reference_yaml():
     assert list(p.ExtrinsicLiDARtoPoseBase) == [1.0 if i % 5 == 0 else 0.0 for i in range(16)]
     s = removert.selfremovert_schedule([2.5, 2.0])
     assert [o for o, _ in s] == [0, 1, 0, 0, 1, 0] and abs(s[1][1] - 2.375) < 1e-6
+
+
+def test_pcl_adapter_builds_against_stand_in_headers(tmp_path):
+    """include/ltr_pcl_adapter.hpp (the glue a ROS build of the node would include) compiles against the stand-in PCL /
+    Eigen headers, links against both libraries, and its host-side conversions round-trip."""
+    import subprocess
+    exe = str(tmp_path / "adapter_check")
+    libdir = os.path.join(ROOT, "lt_mapper_b200")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "oracle", "ref_shim", "include"), os.path.join(ROOT, "tests", "adapter_check.cpp"),
+                           "-o", exe, "-L", libdir, "-lltr_removert", "-lltr_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "adapter ok" in out.stdout, out.stdout + out.stderr
