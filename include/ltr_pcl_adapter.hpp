@@ -95,4 +95,27 @@ inline int fetch_cloud(ltrh_removerter* r, const char* name, int sess, Cloud& ou
     return rc != LTR_OK ? rc : to_host(ltrh_context(r), h, out, octree_layout);
 }
 
+// a named per-keyframe scan set ("keyframe_scans_updated_", ...) back into the vector of clouds the Session holds (Session.h:39-60)
+template <class CloudPtrVector>
+inline int fetch_scans(ltrh_removerter* r, const char* name, int sess, CloudPtrVector& out) {
+    ltr_scanset h;
+    int rc = ltrh_scanset(r, name, sess, &h);
+    if (rc != LTR_OK) return rc;
+    std::int32_t K = 0;
+    std::int64_t total = 0;
+    rc = ltr_scanset_info(ltrh_context(r), h, &K, &total);
+    if (rc != LTR_OK) return rc;
+    std::vector<float> buf(4 * (std::size_t)(total > 0 ? total : 1));
+    std::vector<std::int64_t> off((std::size_t)K + 1, 0);
+    rc = ltr_scanset_download(ltrh_context(r), h, buf.data(), total, off.data());
+    if (rc != LTR_OK) return rc;
+    out.clear();
+    for (std::int32_t k = 0; k < K; ++k) {
+        typename CloudPtrVector::value_type c(new Cloud());
+        unpack(buf.data() + 4 * off[(std::size_t)k], off[(std::size_t)k + 1] - off[(std::size_t)k], *c);
+        out.push_back(c);
+    }
+    return LTR_OK;
+}
+
 }  // namespace ltr_pcl

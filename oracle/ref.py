@@ -12,17 +12,25 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_ref", "libltremovert_ref.so")
 LIB_OMP_PATH = os.path.join(HERE, "_ref", "libltremovert_ref_omp.so")
+LIB_DROPIN_PATH = os.path.join(HERE, "_ref", "libltremovert_dropin.so")   # reference loaders / writers around libltr_removert.so
 
 _lib_cache = {}
 
 
+def _path(omp):
+    return LIB_DROPIN_PATH if omp == "dropin" else LIB_OMP_PATH if omp else LIB_PATH
+
+
 def available(omp=False):
-    return os.path.exists(LIB_OMP_PATH if omp else LIB_PATH)
+    """omp: False = deterministic parity build, True = OpenMP timing build, "dropin" = the drop-in demonstration library."""
+    return os.path.exists(_path(omp))
 
 
 def _lib(omp=False):
     if omp not in _lib_cache:
-        L = ctypes.CDLL(LIB_OMP_PATH if omp else LIB_PATH)
+        L = ctypes.CDLL(_path(omp))
+        if omp == "dropin":
+            L.ref_dropin_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
         i64, f32, vp, cp, ci = ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int
         L.ref_create.restype = vp
         L.ref_destroy.argtypes = [vp]
@@ -155,6 +163,13 @@ class Removerter:
 
     def run(self):
         _lib(self._omp).ref_run(self._h)
+
+    def dropin_run(self, transform_order=0):
+        """omp="dropin" only: the node's own loaders and writers with Steps 0-3 on the B200 library (oracle/ref_shim/dropin_capi.cpp)."""
+        err = ctypes.create_string_buffer(1024)
+        rc = _lib(self._omp).ref_dropin_run(self._h, transform_order, err, 1024)
+        if rc != 0:
+            raise RuntimeError(f"drop-in run failed ({rc}): {err.value.decode()}")
 
     def stage(self, name):
         if _lib(self._omp).ref_stage(self._h, name.encode()) != 0:

@@ -162,3 +162,37 @@ def test_cascade_through_files_matches_compiled_reference(tmp_path):
             x, y = removert.read_pcd(str(a / f)), removert.read_pcd(str(b / f))
             assert x.shape == y.shape and np.array_equal(x.view(np.uint32), y.view(np.uint32)), (stage, f)
     assert len(removert.read_pcd(str(tmp_path / "gpu2" / "nd_map.pcd"))) > 0 and len(removert.read_pcd(str(tmp_path / "gpu2" / "pd_map.pcd"))) > 0
+
+
+def test_reference_node_with_b200_core(tmp_path, small_pair):
+    """INTEGRATION.md "B" executed: the reference's own Removerter object keeps its loaders (loadSessionInfo, parseKeyframes, loadKeyframes)
+    and writers (saveAllTypeOfScans, savePCDFileBinary); Steps 0-3 run on libltr_removert.so / libltr_b200.so through
+    include/ltr_pcl_adapter.hpp (oracle/ref_shim/dropin_capi.cpp).  The files it writes equal the files of the unmodified reference run."""
+    from oracle import ref
+    if not (ref.available() and ref.available("dropin")):
+        pytest.skip("oracle/_ref libraries not built")
+    c, q = small_pair
+    _write_session(tmp_path / "central", c)
+    _write_session(tmp_path / "query", q)
+    ext = [0.955336489125606, -0.29552020666133955, 0.0, 0.5, 0.29552020666133955, 0.955336489125606, 0.0, -0.2, 0.0, 0.0, 1.0, 1.1, 0.0, 0.0, 0.0, 1.0]
+
+    def params(out):
+        return dict(sequence_vfov=50.0, sequence_hfov=360.0, keyframe_gap=1, start_idx=1, end_idx=4, downsample_voxel_size=0.05,
+                    num_nn_points_within=2, dist_nn_points_within=0.01, saveMapPCD=True, save_pcd_directory=str(out), ExtrinsicLiDARtoPoseBase=ext,
+                    central_sess_scan_dir=f"{tmp_path}/central/Scans/", central_sess_pose_path=f"{tmp_path}/central/poses.txt",
+                    query_sess_scan_dir=f"{tmp_path}/query/Scans/", query_sess_pose_path=f"{tmp_path}/query/poses.txt")
+    out_ref, out_b200 = tmp_path / "out_ref", tmp_path / "out_b200"
+    R = ref.Removerter(params(out_ref), transform_order=1)
+    R.run()
+    R.close()
+    D = ref.Removerter(params(out_b200), transform_order=1, omp="dropin")
+    D.dropin_run(transform_order=1)
+    D.close()
+
+    def tree(d):
+        return sorted(os.path.relpath(os.path.join(p, f), d) for p, _, fs in os.walk(d) for f in fs)
+    files = tree(out_ref)
+    assert files == tree(out_b200) and len(files) >= 14 + 5 * 3
+    for f in files:
+        a, b = removert.read_pcd(str(out_ref / f)), removert.read_pcd(str(out_b200 / f))
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), f
