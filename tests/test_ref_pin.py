@@ -353,3 +353,69 @@ def test_full_run_on_other_scenes_matches_the_reference(scratch, seed, beams, az
         assert len(got) == len(exp) == 5 and all(bits_equal(a, b) for a, b in zip(got, exp)), name
     assert len(R.cloud("map_global_curr_dynamic_", 0)) > 0
     R.close()
+
+
+def test_property_random_clouds_match_the_reference():
+    """Property test (hypothesis): arbitrary finite float32 clouds -- including zeros, signed zeros, denormals, huge and tiny magnitudes,
+    duplicated points -- give bit-identical cart2sph values and range / index images in the compiled reference and in the oracle."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    f32 = st.floats(width=32, allow_nan=False, allow_infinity=False, min_value=-1e6, max_value=1e6)
+    special = st.sampled_from([0.0, -0.0, 1e-38, -1e-38, 1e-45, 1.0, -1.0, 100.0, -100.0, 1e6, 3.4e5, 2.5, 0.5])
+    coord = st.one_of(f32, special)
+    pts = st.lists(st.tuples(coord, coord, coord), min_size=1, max_size=200)
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(pts, st.sampled_from([(5, 36), (20, 144), (125, 900), (150, 1080)]), st.booleans())
+    def check(p, shape, dup):
+        a = np.array(p, np.float32).reshape(-1, 3)
+        if dup:
+            a = np.concatenate([a, a[::-1]])
+        cloud = np.concatenate([a, np.zeros((len(a), 1), np.float32)], 1)
+        got = ref.cart2sph(a)
+        x, y, z = a[:, 0], a[:, 1], a[:, 2]
+        with np.errstate(all="ignore"):
+            assert bits_equal(got[:, 0], oracle.atan2f(y, x))
+            assert bits_equal(got[:, 1], oracle.atan2f(z, np.sqrt(x * x + y * y)))
+            assert bits_equal(got[:, 2], np.sqrt(x * x + y * y + z * z))
+        rows, cols = shape
+        er, ei = oracle.map2rimg(cloud, rows, cols)
+        gr, gi = ref.map2rimg(cloud, rows, cols)
+        assert bits_equal(gr, er) and bits_equal(gi, ei)
+    check()
+
+
+def test_property_random_passes_match_the_reference(scratch):
+    """Property test: small random maps and scans (not geometrically consistent, coarse images so that pixels collide, duplicated points so that
+    ranges tie) through the three pass variants of the compiled reference and of the oracle: identical dynamic index sets."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    R = ref.Removerter(base_params(scratch), write_files=False)
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(0, 2**31 - 1), st.integers(3, 400), st.sampled_from([0.2, 0.5, 1.0, 2.5]), st.sampled_from([0, 1, 2]), st.booleans())
+    def check(seed, n, alpha, mode, ties):
+        rng = np.random.default_rng(seed)
+        m = np.concatenate([rng.normal(0, 15, (n, 3)), rng.uniform(0, 1, (n, 1))], 1).astype(np.float32)
+        if ties:
+            m = np.concatenate([m, m[: n // 2]])
+        K = 2
+        scans = []
+        for _ in range(K):
+            ns = int(rng.integers(1, 300))
+            scans.append(np.concatenate([rng.normal(0, 15, (ns, 3)), np.zeros((ns, 1))], 1).astype(np.float32))
+        xyzi = np.concatenate(scans); off = np.concatenate([[0], np.cumsum([len(s) for s in scans])]).astype(np.int64)
+        poses = np.stack([np.eye(4) for _ in range(K)])
+        for k in range(K):
+            a = rng.uniform(-np.pi, np.pi)
+            poses[k][:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+            poses[k][:3, 3] = rng.normal(0, 5, 3)
+        R.load_session_mem(0, xyzi, off, poses)
+        R.load_session_mem(1, xyzi, off, poses)
+        R.set_scans("keyframe_scans_static_projected_", xyzi, off, 1)
+        inv = np.stack([ref.inverse4x4(p) for p in poses])
+        rows, cols = oracle.reset_rimg_size(alpha)
+        R.set_cloud(["map_global_curr_", "map_global_nd_", "map_global_pd_"][mode], m, 0)
+        got = R.dynamic_idx(mode, 0, 1 if mode else 0, rows, cols, len(m))
+        exp = oracle.remove_pass(m, xyzi, off, inv, [oracle.MODE_HD, oracle.MODE_ND, oracle.MODE_PD][mode], alpha, 0.1)
+        assert np.array_equal(got, np.flatnonzero(exp))
+    check()
+    R.close()
