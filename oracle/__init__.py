@@ -34,6 +34,8 @@ def _lib():
         i64, f32, f64, vp, ci, cp = ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p
         L.ltro_atan2f_selfcheck.restype = i64
         L.ltro_atan2f_selfcheck.argtypes = [ctypes.c_uint64, i64]
+        L.ltro_atan2f_selfcheck_wide.restype = i64
+        L.ltro_atan2f_selfcheck_wide.argtypes = [ctypes.c_uint64, i64]
         L.ltro_atan2f.argtypes = [vp, vp, vp, i64]
         L.ltro_libm_atan2f.argtypes = [vp, vp, vp, i64]
         L.ltro_reset_rimg_size.argtypes = [f32, f32, f32, vp, vp]
@@ -82,6 +84,11 @@ def _f64(a):
 
 def max_threads():
     return _lib().ltro_max_threads()
+
+
+def atan2f_selfcheck_wide(seed, n):
+    """bit mismatches between ref_atan2f and the container's libm over log-uniform magnitudes 2^-40 .. 2^40 (branch thresholds)."""
+    return _lib().ltro_atan2f_selfcheck_wide(seed, n)
 
 
 def atan2f_selfcheck(seed, n):

@@ -75,6 +75,24 @@ int64_t ltro_atan2f_selfcheck(uint64_t seed, int64_t n) {
     }
     return bad;
 }
+// the same over log-uniform magnitudes (|x|, |y| in 2^-40 .. 2^40, random signs): ratios far beyond what scan geometry produces,
+// where the branch thresholds of atanf / atan2f live (|y/x| >= 2^25, < 2^-29, exponent difference > 60 ...)
+int64_t ltro_atan2f_selfcheck_wide(uint64_t seed, int64_t n) {
+    int64_t bad = 0;
+    uint64_t s = seed * 0x9e3779b97f4a7c15ull + 7;
+    auto next = [&s]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+    auto draw = [&]() {
+        const uint64_t r = next();
+        const uint32_t e = 127u - 40u + (uint32_t)((r >> 40) % 81u);
+        const uint32_t bits = ((uint32_t)(r & 1u) << 31) | (e << 23) | (uint32_t)((r >> 8) & 0x7fffffu);
+        return u2f(bits);
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        const float x = draw(), y = draw();
+        if (f2u(atan2f(y, x)) != f2u(ref_atan2f(y, x))) ++bad;
+    }
+    return bad;
+}
 void ltro_reset_rimg_size(float vfov, float hfov, float alpha, int* rows, int* cols) { resetRimgSize(vfov, hfov, alpha, rows, cols); }
 void ltro_pixel_index(const float* xyz, int64_t n, int stride, float vfov, float hfov, int rows, int cols, int* row, int* col, float* range) {
     for (int64_t i = 0; i < n; ++i) {

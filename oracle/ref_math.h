@@ -36,7 +36,8 @@ static inline float ref_atanf(float x) {
     const int32_t hx = (int32_t)f2u(x);
     const int32_t ix = hx & 0x7fffffff;
     int id;
-    if (ix >= 0x4c800000) {  // |x| >= 2^26
+    if (ix >= 0x4c000000) {  // |x| >= 2^25 (glibc 2.39's s_atanf.c; measured on this container's libm: atanf(2^25 - 2) takes the
+                             // polynomial path, atanf(2^25) returns atanhi[3] + atanlo[3]; FreeBSD's msun uses 2^26 here)
         if (ix > 0x7f800000) return x + x;  // NaN
         return (hx > 0) ? atanhi[3] + atanlo[3] : -atanhi[3] - atanlo[3];
     }

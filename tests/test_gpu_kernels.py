@@ -31,6 +31,11 @@ def test_device_math_bit_exact(ctx):
     xyz[:len(edge)] = edge
     # near-sensor and grazing points
     xyz[100:100000] *= rng.uniform(0.001, 0.1, (99900, 1)).astype(np.float32)
+    # log-uniform magnitudes 2^-30 .. 2^30 per coordinate: ratios around atanf's branch thresholds (|y/x| >= 2^25, < 2^-29)
+    m = 200000
+    wide = (np.exp2(rng.uniform(-30, 30, (m, 3))) * rng.choice([-1.0, 1.0], (m, 3))).astype(np.float32)
+    wide[:4] = [[0.0078125, 340000.0, 0.0], [1.0, 2.0**25, 0.0], [1.0, 2.0**25 - 2, 0.0], [0.0, 0.0078125, 340000.0]]
+    xyz[100000:100000 + m] = wide
     for alpha in (2.5, 3.0, 1.425):
         rows, cols = oracle.reset_rimg_size(alpha)
         assert (rows, cols) == ltr.reset_rimg_size(alpha)

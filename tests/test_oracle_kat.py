@@ -33,6 +33,13 @@ def test_atan2f_equals_libm():
     """ref_atan2f (fdlibm restatement) is bit-identical to this machine's glibc atan2f on the cart2sph call pattern."""
     n = int(os.environ.get("LTR_ATAN_SAMPLES", "20000000"))
     assert oracle.atan2f_selfcheck(12345, n) == 0
+    # log-uniform magnitudes 2^-40 .. 2^40: the branch thresholds (a property test against the compiled reference found the restatement
+    # using FreeBSD's |x| >= 2^26 where glibc 2.39 switches to atanhi[3] + atanlo[3] at 2^25)
+    assert oracle.atan2f_selfcheck_wide(1, n // 4) == 0
+    edge = np.array([2.0**25 - 2, 2.0**25, 2.0**25 + 4, 2.0**26 - 4, 2.0**26, 4.352e7, 2.0**-29, 2.0**-30, 7.4082805e6], np.float32)
+    one = np.ones_like(edge)
+    for yy, xx in ((edge, one), (-edge, one), (edge, -one), (one, edge), (edge * 0.0078125, one * 0.0078125)):
+        assert np.array_equal(oracle.atan2f(yy, xx).view(np.uint32), oracle.atan2f(yy, xx, libm=True).view(np.uint32))
     # special values
     sp = np.array([0.0, -0.0, 1.0, -1.0, 1e-30, -1e-30, 1e30, -1e30, np.inf, -np.inf, 0.4375, 0.6875, 1.1875, 2.4375, 3e-10], np.float32)
     y, x = np.meshgrid(sp, sp)
