@@ -63,6 +63,7 @@ def _lib(omp=False):
         L.ref_scans_count.argtypes = [vp, ci, cp]
         L.ref_scan.argtypes = [vp, ci, cp, ci, vp, i64]; L.ref_scan.restype = i64
         L.ref_set_scans.argtypes = [vp, ci, cp, vp, vp, ci]
+        L.ref_extract_knn_diff.argtypes = [vp, ci, ci, vp, i64, ci, f32]
         L.ref_load_session_mem.argtypes = [vp, ci, vp, vp, vp, ci]
         L.ref_saved_get.argtypes = [ci, cp, ci, vp, i64]; L.ref_saved_get.restype = i64
         _lib_cache[omp] = L
@@ -251,6 +252,11 @@ class Removerter:
         x = _f32(xyzi); o = np.ascontiguousarray(offsets, np.int64)
         if _lib(self._omp).ref_set_scans(self._h, sess, name.encode(), x.ctypes.data, o.ctypes.data, len(o) - 1) != 0:
             raise KeyError(name)
+
+    def extract_knn_diff(self, sess, target_xyzi, k, thr, low=True):
+        """Session::extractLowDynPointsViaKnnDiff (low) / extractHighDynPointsViaKnnDiff of `sess` against target_xyzi."""
+        t = _f32(target_xyzi)
+        _lib(self._omp).ref_extract_knn_diff(self._h, sess, int(low), t.ctypes.data, len(t), k, thr)
 
     def scans(self, name, sess=0):
         L = _lib(self._omp)

@@ -326,6 +326,18 @@ void ref_load_session_mem(void* h, int sess, const float* xyzi, const int64_t* o
     }
 }
 
+// Session::extractLowDynPointsViaKnnDiff (Session.cpp:393-427; reads keyframe_scans_static_projected_) / extractHighDynPointsViaKnnDiff
+// (:487-504; reads keyframe_scans_) of session `sess` against a target map given by value; k / thr are the per-object copies of
+// removert/num_nn_points_within and dist_nn_points_within (every Session is its own RosParamServer).
+int ref_extract_knn_diff(void* h, int sess, int low, const float* target_xyzi, int64_t n, int k, float thr) {
+    Session& S = sess_of((Removerter*)h, sess);
+    S.kNumKnnPointsToCompare = k;
+    S.kScanKnnAndMapKnnAvgDiffThreshold = thr;
+    PC::Ptr t = make_cloud(target_xyzi, n);
+    if (low) S.extractLowDynPointsViaKnnDiff(t); else S.extractHighDynPointsViaKnnDiff(t);
+    return 0;
+}
+
 // ---- what the run wrote through pcl::io::savePCDFileBinary ----
 void ref_saved_clear() { ltr_shim::saved().clear(); }
 int ref_saved_count() { return (int)ltr_shim::saved().size(); }

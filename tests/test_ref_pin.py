@@ -419,3 +419,48 @@ def test_property_random_passes_match_the_reference(scratch):
         assert np.array_equal(got, np.flatnonzero(exp))
     check()
     R.close()
+
+
+def test_property_knn_partition_matches_the_reference(scratch):
+    """Property test: Session::extractLowDynPointsViaKnnDiff / extractHighDynPointsViaKnnDiff (Session.cpp:393-427, 487-504, 537-642) on random
+    scans, targets, k, thresholds, poses and extrinsics: the coexist / diff partitions equal the oracle's knn_partition bit for bit (this covers
+    the squared-distance mean, the double accumulate, the strict threshold and the base2lidar matrix the reference passes to local2global)."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(0, 2**31 - 1), st.sampled_from([1, 2, 3]), st.sampled_from([0.01, 0.04, 0.5, 4.0]), st.booleans(), st.booleans(), st.sampled_from([0, 1]))
+    def check(seed, k, thr, low, use_ext, order):
+        rng = np.random.default_rng(seed)
+        l2b = EXT if use_ext else np.eye(4)
+        R = ref.Removerter(base_params(scratch, l2b), transform_order=order, write_files=False)
+        K = 2
+        scans = []
+        for _ in range(K):
+            ns = int(rng.integers(1, 400))
+            scans.append(np.concatenate([rng.normal(0, 3, (ns, 3)), rng.uniform(0, 1, (ns, 1))], 1).astype(np.float32))
+        xyzi = np.concatenate(scans); off = np.concatenate([[0], np.cumsum([len(s) for s in scans])]).astype(np.int64)
+        poses = np.stack([np.eye(4) for _ in range(K)])
+        for j in range(K):
+            a = rng.uniform(-np.pi, np.pi)
+            poses[j][:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+            poses[j][:3, 3] = rng.normal(0, 2, 3)
+        nt = int(rng.integers(k, 600))
+        target = np.concatenate([rng.normal(0, 3, (nt, 3)), np.zeros((nt, 1))], 1).astype(np.float32)
+        # a few target points next to where the first scan lands in the map frame, so that both partitions are non-empty
+        g = oracle.transform(oracle.transform(scans[0], oracle.inverse4x4(l2b), order), poses[0], order)
+        m = min(nt, len(g), 50)
+        target[:m, :3] = g[:m, :3] + rng.normal(0, 0.05, (m, 3)).astype(np.float32)
+        R.load_session_mem(0, xyzi, off, poses)
+        R.set_scans("keyframe_scans_static_projected_", xyzi, off, 0)
+        R.extract_knn_diff(0, target, k, thr, low=low)
+        if low:
+            co, di = R.scans("scans_knn_coexist_", 0), R.scans("scans_knn_diff_", 0)
+        else:
+            co, di = None, R.scans("keyframe_scans_dynamic_", 0)
+        for j in range(K):
+            _, eco, edi = oracle.knn_partition(scans[j], poses[j], ref.inverse4x4(poses[j]), target, k, thr, lidar2base=l2b, order=order)
+            assert bits_equal(di[j], edi), (j, "diff")
+            if co is not None:
+                assert bits_equal(co[j], eco), (j, "coexist")
+        R.close()
+    check()
