@@ -365,8 +365,8 @@ def test_property_random_clouds_match_the_reference():
     pts = st.lists(st.tuples(coord, coord, coord), min_size=1, max_size=200)
 
     @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
-    @given(pts, st.sampled_from([(5, 36), (20, 144), (125, 900), (150, 1080)]), st.booleans())
-    def check(p, shape, dup):
+    @given(pts, st.sampled_from([0.1, 0.4, 2.5, 3.0]), st.booleans())
+    def check(p, alpha, dup):
         a = np.array(p, np.float32).reshape(-1, 3)
         if dup:
             a = np.concatenate([a, a[::-1]])
@@ -377,10 +377,15 @@ def test_property_random_clouds_match_the_reference():
             assert bits_equal(got[:, 0], oracle.atan2f(y, x))
             assert bits_equal(got[:, 1], oracle.atan2f(z, np.sqrt(x * x + y * y)))
             assert bits_equal(got[:, 2], np.sqrt(x * x + y * y + z * z))
-        rows, cols = shape
+        rows, cols = oracle.reset_rimg_size(alpha)
         er, ei = oracle.map2rimg(cloud, rows, cols)
         gr, gi = ref.map2rimg(cloud, rows, cols)
         assert bits_equal(gr, er) and bits_equal(gi, ei)
+        # parseProjectedPoints (utility.cpp:74-89): row-major emission, the point with index 0 is never emitted
+        cloud[:, 3] = np.arange(len(cloud), dtype=np.float32)
+        exp, idx = oracle.parse_projected(cloud, np.eye(4), alpha)
+        loc = ref.transform_global_to_local(cloud, np.eye(4), np.eye(4))   # as Session::parseScansViaProjection does (turns -0.0 into +0.0)
+        assert bits_equal(ref.parse_projected(loc, rows, cols), exp) and 0 not in idx
     check()
 
 
