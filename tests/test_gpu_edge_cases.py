@@ -148,3 +148,43 @@ def test_error_paths_release_their_scratch_memory(ctx):
     ctx.remove_pass(hg, ss, ps, ltr.MODE_HD, 2.5)
     ctx.cloud_free(ctx.voxel_centroid(hg, 0.1))
     assert ctx.memory_stats()[0] == before                     # steady state: scratch goes back to the cache
+
+
+def test_randomised_small_passes_match_the_oracle():
+    """Many tiny random scenes (not geometrically consistent; coarse images so pixels collide, duplicated points so ranges tie, signed zeros,
+    points on the sensor axis) through every pass variant and the visible-point extraction: flags / points equal the oracle's (whose
+    behaviour on exactly such inputs is pinned against the compiled reference by the property tests in tests/test_ref_pin.py)."""
+    rng = np.random.default_rng(2024)
+    with ltr.Context() as ctx, ltr.Context(fast_path=False) as ctx_exact:
+        for case in range(60):
+            n = int(rng.integers(3, 500))
+            m = np.concatenate([rng.normal(0, 15, (n, 3)), rng.uniform(0, 1, (n, 1))], 1).astype(np.float32)
+            if case % 3 == 0:
+                m = np.concatenate([m, m[: n // 2]])                                   # exact range ties
+            if case % 5 == 0:
+                m[: min(4, len(m)), :3] = [[0.0, 0.0, 0.0], [-0.0, 0.0, 0.0], [0.0, 0.0, 2.0], [0.0, -0.0, -3.0]][: min(4, len(m))]
+            K = int(rng.integers(1, 4))
+            scans = []
+            for _ in range(K):
+                ns = int(rng.integers(0, 300))
+                scans.append(np.concatenate([rng.normal(0, 15, (ns, 3)), np.zeros((ns, 1))], 1).astype(np.float32))
+            xyzi = np.concatenate(scans) if sum(map(len, scans)) else np.zeros((0, 4), np.float32)
+            off = np.concatenate([[0], np.cumsum([len(s) for s in scans])]).astype(np.int64)
+            poses = np.stack([np.eye(4) for _ in range(K)])
+            for k in range(K):
+                a = rng.uniform(-np.pi, np.pi)
+                poses[k][:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+                poses[k][:3, 3] = rng.normal(0, 5, 3)
+            inv = oracle.inverse_poses(poses)
+            alpha = [0.2, 0.5, 1.0, 2.5][case % 4]
+            for c in (ctx, ctx_exact):
+                mh = c.cloud_upload(m); ss = c.scanset_upload(xyzi, off); ps = c.poses_upload(poses, inv)
+                for mode, omode in ((ltr.MODE_HD, oracle.MODE_HD), (ltr.MODE_ND, oracle.MODE_ND), (ltr.MODE_PD, oracle.MODE_PD)):
+                    exp = oracle.remove_pass(m, xyzi, off, inv, omode, alpha, 0.1)
+                    c.remove_pass(mh, ss, ps, mode, alpha)
+                    assert np.array_equal(c.flags_download(mh), exp), (case, mode, c is ctx)
+                pts, po = c.scanset_download(c.parse_projected(mh, ps, 0, K, alpha))
+                for k in range(K):
+                    e, _ = oracle.parse_projected(m, inv[k], alpha)
+                    assert np.array_equal(pts[po[k]:po[k + 1]].view(np.uint32), e.view(np.uint32)), (case, k, c is ctx)
+                c.cloud_free(mh)
