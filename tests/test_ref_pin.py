@@ -469,3 +469,42 @@ def test_property_knn_partition_matches_the_reference(scratch):
                 assert bits_equal(co[j], eco), (j, "coexist")
         R.close()
     check()
+
+
+def test_property_keyframe_selection_and_pose_files_match_the_reference(tmp_path_factory, scratch):
+    """Property test of the product's host logic (lt_mapper_b200/csrc/host/io.cpp) against the reference's Session::loadSessionInfo /
+    parseKeyframes / parseKeyframesInROI (Session.cpp:80-118, 138-174, 230-263): random scan counts, index ranges (including empty and
+    out-of-range ones), gaps, trajectories, and pose lines written in several number formats with 12 or 16 values."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(0, 2**31 - 1), st.integers(1, 40), st.integers(1, 40), st.integers(-3, 45), st.integers(-3, 45), st.integers(1, 7))
+    def check(seed, nc, nq, start, end, gap):
+        rng = np.random.default_rng(seed)
+        counter[0] += 1
+        root = str(tmp_path_factory.mktemp(f"kf{counter[0]}"))
+        poses = {}
+        for name, n in (("central", nc), ("query", nq)):
+            os.makedirs(f"{root}/{name}/scans")
+            P = np.stack([np.eye(4) for _ in range(n)])
+            P[:, :3, 3] = np.cumsum(rng.normal(0, 3.0, (n, 3)), 0) + (rng.normal(0, 8, 3) if name == "query" else 0)
+            poses[name] = P
+            with open(f"{root}/{name}/poses.txt", "w") as f:
+                for k in range(n):
+                    open(f"{root}/{name}/scans/{k:06d}.pcd", "w").close()        # only the names matter before loadKeyframes
+                    vals = P[k].ravel() if rng.random() < 0.3 else P[k][:3].ravel()   # 16 or 12 values per line (Session.cpp:106-108)
+                    fmt = rng.integers(0, 3)
+                    f.write(" ".join(repr(float(v)) if fmt == 0 else f"{v:.17e}" if fmt == 1 else f"{v:.17g}" for v in vals) + "\n")
+        R = ref.Removerter(base_params(root, start_idx=start, end_idx=end, keyframe_gap=gap, save_pcd_directory=scratch + "/"), write_files=False)
+        R.stage("loadSessionInfo"); R.stage("parseKeyframes")
+        pc = removert.read_poses(f"{root}/central/poses.txt"); pq = removert.read_poses(f"{root}/query/poses.txt")
+        assert bits_equal(pc, poses["central"]) and bits_equal(pq, poses["query"])
+        exp_c = list(removert.parse_keyframes(nc, start, end, gap))
+        assert R.keyframe_names(0) == [f"{k:06d}.pcd" for k in exp_c]
+        kc = R.keyframe_poses(0)[0]
+        assert bits_equal(kc, pc[exp_c].reshape(-1, 4, 4))
+        exp_q = list(removert.parse_keyframes_in_roi(pq, kc, gap))
+        assert R.keyframe_names(1) == [f"{k:06d}.pcd" for k in exp_q]
+        R.close()
+    check()
