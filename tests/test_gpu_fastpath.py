@@ -142,3 +142,4 @@ def test_scan_range_image_fast_equals_exact(small_pair, vfov, hfov):
                     exp = oracle.scan2rimg(xyzi[off[k]:off[k + 1]], rows, cols, vfov, hfov)
                     got = ctx.debug_scan_rimg(ss, k, alpha)
                     assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (fast, alpha, k)
+

@@ -508,3 +508,38 @@ def test_property_keyframe_selection_and_pose_files_match_the_reference(tmp_path
         assert R.keyframe_names(1) == [f"{k:06d}.pcd" for k in exp_q]
         R.close()
     check()
+
+
+def test_points_on_pixel_boundaries_land_in_the_reference_pixel():
+    """The most rounding-sensitive inputs: points whose azimuth / elevation sit on a pixel boundary (pre-round coordinate = n + 0.5) and their
+    float neighbours a few ulps either side.  Each point is projected alone through the reference's map2RangeImg; the pixel it lands in (and
+    the range stored there) must be the oracle's."""
+    rng = np.random.default_rng(5)
+    for (vfov, hfov, alpha), count in (((50.0, 360.0, 0.4), 1500), ((50.0, 360.0, 2.5), 400), ((33.2, 180.0, 1.0), 400)):
+        rows, cols = oracle.reset_rimg_size(alpha, vfov, hfov)
+        pts = []
+        for _ in range(count):
+            r = rng.uniform(0.5, 90.0)
+            if rng.random() < 0.5:      # column boundary, arbitrary elevation inside the field of view
+                az = np.deg2rad((rng.integers(0, cols) + 0.5) / cols * hfov - hfov / 2)
+                el = np.deg2rad(rng.uniform(-vfov / 2, vfov / 2))
+            else:                       # row boundary, arbitrary azimuth
+                az = np.deg2rad(rng.uniform(-hfov / 2, hfov / 2))
+                el = np.deg2rad(vfov / 2 - (rng.integers(0, rows) + 0.5) / rows * vfov)
+            p = np.array([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el)], np.float32)
+            for _ in range(int(rng.integers(0, 4))):   # walk a few ulps in a random coordinate
+                j = int(rng.integers(0, 3))
+                p[j] = np.nextafter(p[j], np.float32(np.inf if rng.random() < 0.5 else -np.inf))
+            pts.append(p)
+        pts = np.array(pts, np.float32)
+        er, ec, erng = oracle.pixel_index(pts, rows, cols, vfov, hfov)
+        first = np.array([[1.0, 0.0, 0.0, 0.0]], np.float32)     # index 0 is "no point" in the index image: keep a dummy there
+        moved = 0
+        for i, p in enumerate(pts):
+            cloud = np.concatenate([first * 1e3, np.concatenate([p, [0.0]]).astype(np.float32)[None]])   # dummy far away at az = el = 0
+            gr, gi = ref.map2rimg(cloud, rows, cols, vfov, hfov)
+            rr, cc = np.argwhere(gi == 1)[0] if (gi == 1).any() else (-1, -1)
+            assert (rr, cc) == (er[i], ec[i]), (i, p, (rr, cc), (er[i], ec[i]))
+            assert gr[rr, cc].view(np.uint32) == erng[i].view(np.uint32)
+            moved += 1
+        assert moved == count
