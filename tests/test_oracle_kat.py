@@ -221,3 +221,22 @@ def test_faithful_mode_matches_exact_mode_single_thread(small_pair):
     for a, b in zip(res[0][:-1], res[1][:-1]):
         assert np.array_equal(a, b)
     assert res[0][-1] == res[1][-1]
+
+
+def test_flag_set_is_invariant_under_keyframe_order_and_sharding(small_pair, small_maps):
+    """SURVEY §4 properties on the oracle: the dynamic index set of a pass does not depend on the order in which the source keyframes
+    are visited, and the union of the sets of any keyframe partition (what the ranks of a multi-GPU run compute) equals the whole."""
+    c = small_pair[0]
+    m = small_maps[0]
+    inv = oracle.inverse_poses(c.poses)
+    rng = np.random.default_rng(0)
+    for mode in (oracle.MODE_HD, oracle.MODE_ND, oracle.MODE_PD):
+        full = oracle.remove_pass(m, c.xyzi, c.offsets, inv, mode, 2.5)
+        perm = rng.permutation(c.K)
+        xyzi = np.concatenate([c.scan(k) for k in perm]); off = np.concatenate([[0], np.cumsum([len(c.scan(k)) for k in perm])]).astype(np.int64)
+        assert np.array_equal(oracle.remove_pass(m, xyzi, off, inv[perm], mode, 2.5), full)
+        union = np.zeros_like(full)
+        for part in (perm[:2], perm[2:3], perm[3:]):
+            x = np.concatenate([c.scan(k) for k in part]); o = np.concatenate([[0], np.cumsum([len(c.scan(k)) for k in part])]).astype(np.int64)
+            union |= oracle.remove_pass(m, x, o, inv[part], mode, 2.5)
+        assert np.array_equal(union, full) and full.sum() > 0
