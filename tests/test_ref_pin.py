@@ -543,3 +543,31 @@ def test_points_on_pixel_boundaries_land_in_the_reference_pixel():
             assert gr[rr, cc].view(np.uint32) == erng[i].view(np.uint32)
             moved += 1
         assert moved == count
+
+
+def test_full_size_scans_match_the_reference(scratch):
+    """BASELINE-sized scans (64 x 1800 rays, ~103 k returns each), 3 keyframes per session, the bench's schedule and kNN setting: every
+    cloud the compiled reference holds after Steps 0-2 equals the oracle's (the dense, full-resolution counterpart of the small-scene tests)."""
+    import synth
+    sched = [(0, 2.5), (0, 2.0), (0, 1.5), (1, 1.0)]
+    pair = synth.make_pair(3)
+    R = ref.Removerter(base_params(scratch, num_nn_points_within=1, dist_nn_points_within=0.04), write_files=False)
+    O = oracle.Removerter(schedule=sched, num_knn=1, knn_thr=0.04, threads=8)
+    for s, d in enumerate(pair):
+        R.load_session_mem(s, d.xyzi, d.offsets, d.poses)
+        O.load_session(s, d.xyzi, d.offsets, d.poses, np.stack([ref.inverse4x4(p) for p in d.poses]))
+    for st in ("precleaningKeyframes", "makeGlobalMap"):
+        R.stage(st); O.stage(st)
+    R.high_dyn_with_schedule(sched)
+    O.stage("removeHighDynamicPoints")
+    for st in ("parseStaticScansViaProjection", "detectLowDynamicPoints"):
+        R.stage(st); O.stage(st)
+    for s in (0, 1):
+        for name in ("map_global_orig_", "map_global_curr_", "map_global_curr_static_", "map_global_curr_dynamic_", "map_global_nd_", "map_global_nd_strong_",
+                     "map_global_nd_weak_", "map_global_pd_", "map_global_pd_strong_", "map_global_pd_weak_"):
+            assert bits_equal(R.cloud(name, s), O.cloud(name, s)), (name, s)
+        for name in ("keyframe_scans_", "keyframe_scans_dynamic_", "keyframe_scans_static_projected_", "scans_knn_coexist_", "scans_knn_diff_"):
+            got, exp = R.scans(name, s), O.clouds(name, s)
+            assert len(got) == len(exp) == 3 and all(bits_equal(a, b) for a, b in zip(got, exp)), (name, s)
+    assert len(R.cloud("map_global_orig_", 0)) > 250000 and len(R.cloud("map_global_curr_dynamic_", 0)) > 0
+    R.close()
