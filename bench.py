@@ -1,20 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- keyframes/sec of the LT-removert + two-session diff hot path on B200 (BASELINE.json metric).
 
-One "step" = Step 1 + static projection + Step 2 of Removerter::run() (ltremovert/src/Removerter.cpp:1665-1669:
-removeHighDynamicPoints, parseStaticScansViaProjection, detectLowDynamicPoints) over one synthetic two-session pair.
-Workload (BASELINE.json configs[1]): 200 keyframes per session PER GPU, 64 beams x 1800 steps (~103 k returns/scan),
-3 remove + 1 revert resolutions, kNN diff k = 1, r = 0.2 m (threshold r^2 = 0.04 on the squared distance).
+Workload = BASELINE.json configs[2] (N = 1) / configs[3] (N > 1, the SAME pair, strong scaling): a 1000-keyframe two-session
+synthetic pair, 64 beams x 1800 steps (~103 k returns per scan), the full Removerter::selfRemovert schedule
+remove(r), revert(0.95 r), remove(r) for r in 2.5, 2.0, 1.5 (ltremovert/src/Removerter.cpp:1378-1393), kNN diff with the
+shipped k = 2 / mean squared distance 0.01 (config/params_ltmapper.yaml:65-66), 3 + 3 strong/weak ND / PD filter passes
+(Removerter.cpp:1395-1411).  One "step" = Step 1 + static projection + Step 2 of Removerter::run() (Removerter.cpp:1665-1669)
+over the whole pair; keyframes = K_central + K_query = 2000.
 
-  python bench.py [--gpus N --steps K --warmup W]            our arm (one process per GPU under torchrun for N > 1)
-  python bench.py --impl reference [...]                      the reference's CPU path (oracle, reference threading)
+  python bench.py [--gpus N --steps K --warmup W]     our arm (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference [...]               the reference's own CPU code on a bounded sample of the same workload
 
-Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the definitions of every field.
+Multi-GPU (N > 1): the pair is sharded by keyframe and, for an even N, by session: ranks [0, N/2) own the central keyframes,
+the others the query keyframes (contiguous blocks in rank order); exchange points are NCCL calls made by the library itself
+(lt_mapper_b200/csrc/nccl_comm.cu).  torch.distributed only hands the NCCL id around, synchronises the timed region and takes
+the max over ranks.
+
+Prints ONE JSON line (rank 0).  DESIGN.md section 7 defines every field.
 """
 import argparse
+import hashlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -24,13 +31,38 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-KF_PER_GPU = 200                                   # keyframes per session per GPU (configs[1])
-SCHEDULE = [(0, 2.5), (0, 2.0), (0, 1.5), (1, 1.0)]  # 3 remove + 1 revert resolutions
-NUM_KNN, KNN_THR = 1, 0.04                         # k = 1, r = 0.2 m  ->  r^2 on the squared distance (Session.cpp:592-596)
-CPU_SAMPLE_KF = 20                                 # keyframes per session of the bounded CPU sample (~10-20 s of CPU work per step)
+KF_PER_SESSION = 1000                              # configs[2] / configs[3]
+RESOLUTIONS = [2.5, 2.0, 1.5]                      # selfRemovert resolutions
+NUM_KNN, KNN_THR = 2, 0.01                         # params_ltmapper.yaml:65-66 (threshold on the MEAN SQUARED distance, Session.cpp:592-596)
 METRIC = "keyframes/sec (two-session removert+diff)"
 LD_OUTPUTS = ["nd_map", "pd_map", "strong_nd_map", "weak_nd_map", "strong_pd_map", "weak_pd_map", "union_map_queryside",
               "union_map_centralside"]
+DIGEST_OUTPUTS = LD_OUTPUTS + ["central_sess_high_dyn", "query_sess_high_dyn"]
+SIZES_PATH = os.path.join(ROOT, "tests", "golden", "config2_pass_sizes.json")
+
+
+def schedule():
+    """[(op, res)]: op 0 = removeOnce, 1 = revertOnce (between resetCurrrentMapAsDynamic / AsStatic), Removerter.cpp:1378-1393;
+    the revert resolution is the double product 0.95 * r narrowed to float once (:1385)."""
+    s = []
+    for r in RESOLUTIONS:
+        s += [(0, r), (1, float(np.float32(0.95 * float(np.float32(r))))), (0, r)]
+    return s
+
+
+def rimg_shape(alpha, vfov=50.0, hfov=360.0):
+    """resetRimgSize (utility.cpp:222-236): int(std::round(float * float)), round half away from zero."""
+    r, c = np.float32(vfov) * np.float32(alpha), np.float32(hfov) * np.float32(alpha)
+    return int(np.floor(np.float64(r) + 0.5)), int(np.floor(np.float64(c) + 0.5))
+
+
+def workload_config(kf):
+    """The `config` object: identical in both arms (same pair, same schedule, same metric region)."""
+    return {"workload": f"configs[2] (N=1) / configs[3] (N>1, same pair keyframe-sharded): {kf}-keyframe two-session synthetic pair, 64x1800 scans "
+                        f"(~103k returns/scan), full selfRemovert remove/revert/remove at {RESOLUTIONS}, kNN diff k={NUM_KNN} thr={KNN_THR}, "
+                        "3+3 strong/weak ND/PD filter passes",
+            "keyframes_per_session": kf, "schedule": [[int(o), float(r)] for o, r in schedule()], "num_knn": NUM_KNN, "knn_thr": KNN_THR,
+            "timed_region": "Step 1 + static projection + Step 2 (Removerter.cpp:1665-1669)"}
 
 
 def measured_peaks():
@@ -82,7 +114,6 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + str(self.err)]}
         self.stop_flag = True
         self.thread.join(timeout=5)
-        nv = self.nv
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                  "hw_power_brake_slowdown": 0x80}
         reasons = set()
@@ -95,16 +126,36 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvml"}
 
 
-def gen_block(rank, kf):
+def owned_blocks(rank, world, kf, split):
+    """{session: (k0, count)} of the keyframes this rank owns: contiguous blocks in rank order (keyframe order == rank order)."""
+    if split:
+        g = world // 2
+        s, r = (0, rank) if rank < g else (1, rank - g)
+        return {s: (r * kf // g, (r + 1) * kf // g - r * kf // g), 1 - s: (0, 0)}
+    return {s: (rank * kf // world, (rank + 1) * kf // world - rank * kf // world) for s in (0, 1)}
+
+
+def gen_blocks(rank, world, kf, split):
     import synth
-    import oracle  # inverse poses only (4x4 double inverse; the C-ABI takes inverse poses as an input)
     threads = max(1, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))))
-    out = []
-    for s in (0, 1):
-        d = synth.make_session(s, kf, k0=rank * kf, threads=threads)
-        out.append((d, np.stack([np.linalg.inv(p) for p in d.poses])))
-    del oracle
+    out = {}
+    for s, (k0, n) in owned_blocks(rank, world, kf, split).items():
+        if n == 0:
+            out[s] = None
+            continue
+        d = synth.make_session(s, n, k0=k0, threads=threads)
+        out[s] = (d, np.stack([np.linalg.inv(p) for p in d.poses]))   # the C-ABI takes inverse poses as an input (ltr_b200.h)
     return out
+
+
+# names used by the older probe scripts under profiles/
+SCHEDULE = schedule()
+KF_PER_GPU = KF_PER_SESSION
+
+
+def gen_block(rank, kf):
+    b = gen_blocks(0, 1, kf, False)
+    return [b[0], b[1]]
 
 
 class _QuietStdout:
@@ -125,91 +176,177 @@ class _QuietStdout:
         os.close(self._saved); os.close(self._dst)
 
 
-def cpu_baseline_run(steps=1, warmup=0):
-    """The reference's CPU path on a bounded sample of the SAME workload: the first CPU_SAMPLE_KF keyframes of each session,
-    same schedule and kNN parameters, Step 1 + static projection + Step 2.
+# -----------------------------------------------------------------------------------------------------------------------------
+# Reference arm / cpu_baseline: the reference's own CPU code on a bounded sample of the SAME workload.
+# -----------------------------------------------------------------------------------------------------------------------------
+class ReferenceSampler:
+    """The full configs[2] step costs the reference hours of CPU time (2000 keyframes x ~20 projections of a 6-21 M point map
+    each), so one bench step of this arm is a bounded SAMPLE of it, built so that nothing but the exactly linear keyframe count
+    is scaled:
 
-    kind "reference": the reference's own ltremovert sources, compiled unmodified behind the third-party stand-ins
-    (oracle/_ref/libltremovert_ref_omp.so, OpenMP pragmas active as in the reference's build; see oracle/ref_shim), driven
-    through its own member functions.  kind "port" (only when that library was not built): the oracle in `faithful` mode
-    (reference threading structure).  Threads: num_omp_cores = min(16, host cores); map2RangeImg hard-codes 16 (utility.cpp:109)."""
-    import synth
-    c, q = synth.make_pair(CPU_SAMPLE_KF)
-    cores = min(16, os.cpu_count() or 1)
-    from oracle import ref
-    use_ref = ref.available(omp=True)
-    times = []
-    for it in range(warmup + steps):
-        if use_ref:
-            import tempfile
-            with tempfile.TemporaryDirectory() as tmp, _QuietStdout():
-                R = ref.Removerter(dict(save_pcd_directory=tmp + "/", sequence_vfov=50.0, sequence_hfov=360.0,
-                                        ExtrinsicLiDARtoPoseBase=np.eye(4).ravel().tolist(), downsample_voxel_size=0.05,
-                                        num_nn_points_within=NUM_KNN, dist_nn_points_within=KNN_THR, num_omp_cores=cores),
-                                   omp=True, write_files=False)
-                for s, d in ((0, c), (1, q)):
-                    R.load_session_mem(s, d.xyzi, d.offsets, d.poses)
-                R.stage("precleaningKeyframes"); R.stage("makeGlobalMap")
-                t0 = time.perf_counter()
-                R.high_dyn_with_schedule(SCHEDULE)
-                R.stage("parseStaticScansViaProjection")
-                R.stage("detectLowDynamicPoints")
-                dt = time.perf_counter() - t0
-                n_map = len(R.cloud("map_global_orig_", 0))
-                R.close()
-        else:
-            import oracle
-            R = oracle.Removerter(num_knn=NUM_KNN, knn_thr=KNN_THR, schedule=SCHEDULE, faithful=True, omp_cores=cores, threads=cores)
-            for s, d in ((0, c), (1, q)):
-                R.load_session(s, d.xyzi, d.offsets, d.poses, np.stack([np.linalg.inv(p) for p in d.poses]))
-            R.run(step0=True, step12=False)
-            t0 = time.perf_counter()
-            R.run(step0=False, step12=True)
-            dt = time.perf_counter() - t0
-            n_map = len(R.cloud("map_global_orig_", 0))
-            del R
-        if it >= warmup:
-            times.append(dt)
-    dt = float(np.mean(times))
-    how = ("the reference's own ltremovert sources compiled behind third-party stand-ins (oracle/_ref, OpenMP on; PCL/FLANN/Eigen calls go to the "
-           "oracle's restatements)" if use_ref else "oracle in reference-threading mode (oracle/_ref not built)")
-    return {"value": 2 * CPU_SAMPLE_KF / dt, "unit": "keyframes/s", "cores": cores, "kind": "reference" if use_ref else "port",
-            "sample": f"first {CPU_SAMPLE_KF} keyframes of each session of the same synthetic pair (64x1800 scans, {n_map} merged points), "
-                      f"same schedule/kNN, Step 1 + static projection + Step 2, {how}; {dt:.2f} s per step. "
-                      f"Cost is O(K*N): per-keyframe CPU cost at the full 200-keyframe map is higher, so this ratio is conservative",
-            "seconds_per_step": dt}
+    * set-up (untimed): the whole 1000-keyframe pair is generated and the reference's own Step 0 (precleaningKeyframes +
+      makeGlobalMap, Removerter.cpp:1660-1662) builds the TRUE full-size maps from all 2 x 1000 scans;
+    * one step (timed): S keyframes of each session (a different, evenly spread subset every step) go through EVERY
+      per-keyframe loop of the step -- the 9 + 9 selfRemovert passes, extractHighDynPointsViaKnnDiff, the static projection,
+      extractLowDynPointsViaKnnDiff, the 3 + 3 ND / PD filter passes and the keyframe merges -- by calling the reference's own
+      member functions (compiled unmodified into oracle/_ref/libltremovert_ref_omp.so, OpenMP on) on maps of the TRUE size of
+      that pass.  The true per-pass map sizes are properties of the workload (tests/golden/config2_pass_sizes.json, the pass log
+      of the device run; tests/test_gpu_fullsize.py checks the device run still produces exactly these, and this class checks
+      that the reference-built full map has exactly the recorded size).  The map given to pass i is the first-N_i-by-stride
+      subset of the reference-built full map: the real pass-i map is also a subset of that map's voxels, so point density and
+      spatial distribution are the real ones;
+    * value = 2 S / (time in those loops): every one of them is exactly linear in the keyframe count, so this IS the
+      reference's keyframes/s on the full workload, minus its per-pass fixed costs (partition, 2 voxelisations, kd-tree
+      construction: ~3 % of its step), which are left out -- that can only make the reference look faster.
+    """
+
+    def __init__(self, kf, S=1, quiet=True):
+        import synth
+        from oracle import ref
+        self.ref, self.kf, self.S = ref, kf, S
+        self.cores = min(16, os.cpu_count() or 1)      # params_ltmapper.yaml:69 num_omp_cores 16; utility.cpp:109 hard-codes 16 for map2RangeImg
+        if not ref.available(omp=True):
+            raise RuntimeError("oracle/_ref/libltremovert_ref_omp.so is missing (built by __graft_entry__.build() where /root/reference is mounted)")
+        with open(SIZES_PATH) as f:
+            self.sizes = json.load(f)
+        if self.sizes["keyframes_per_session"] != kf:
+            raise RuntimeError(f"{SIZES_PATH} records {self.sizes['keyframes_per_session']} keyframes/session, asked for {kf}")
+        t0 = time.perf_counter()
+        self.data = synth.make_pair(kf)
+        self.params = dict(save_pcd_directory="/tmp/ltr_ref_unused/", sequence_vfov=50.0, sequence_hfov=360.0,
+                           ExtrinsicLiDARtoPoseBase=np.eye(4).ravel().tolist(), downsample_voxel_size=0.05, num_nn_points_within=NUM_KNN,
+                           dist_nn_points_within=KNN_THR, num_omp_cores=self.cores)
+        with _QuietStdout():
+            R = ref.Removerter(self.params, omp=True, write_files=False)
+            for s, d in enumerate(self.data):
+                R.load_session_mem(s, d.xyzi, d.offsets, d.poses)
+            R.stage("precleaningKeyframes"); R.stage("makeGlobalMap")          # the reference's own Step 0 on ALL keyframes
+            self.full_map = [R.cloud("map_global_curr_", s) for s in (0, 1)]
+            self.clean_scans = [R.scans("keyframe_scans_", s) for s in (0, 1)]  # precleaned scans, as Step 1 sees them
+            R.close()
+        got = [len(m) for m in self.full_map]
+        if got != self.sizes["map_points"]:
+            raise RuntimeError(f"reference-built full maps have {got} points, the workload table says {self.sizes['map_points']}")
+        self.setup_s = time.perf_counter() - t0
+        self.step_index = 0
+        self.last_breakdown = {}
+
+    def _subset(self, sess, n):
+        """First-n-by-stride subset of the reference-built full map of `sess` (n <= its size): real voxels, real density."""
+        m = self.full_map[sess]
+        if n >= len(m):
+            return m
+        idx = (np.arange(n, dtype=np.int64) * len(m)) // n
+        return m[idx]
+
+    def _load_subset(self, R, ks):
+        for s in (0, 1):
+            scans = [self.clean_scans[s][k] for k in ks]
+            off = np.zeros(len(ks) + 1, np.int64)
+            off[1:] = np.cumsum([len(a) for a in scans])
+            R.load_session_mem(s, np.concatenate(scans), off, self.data[s].poses[list(ks)])
+
+    def step(self):
+        """One bounded sample; returns (seconds in the reference's per-keyframe loops, keyframes processed)."""
+        ref, S, kf = self.ref, self.S, self.kf
+        j = self.step_index
+        self.step_index += 1
+        ks = [(7 + 37 * j + i * (kf // S)) % kf for i in range(S)]
+        bd = {}
+        t_total = 0.0
+        with _QuietStdout():
+            R = ref.Removerter(self.params, omp=True, write_files=False)
+            self._load_subset(R, ks)
+            # Step 1: 9 selfRemovert passes per session on maps of the true per-pass size
+            for s in (0, 1):
+                for (op, res), n in zip(schedule(), self.sizes["hd_pass_map_points"][s]):
+                    R.set_cloud("map_global_curr_", self._subset(s, n), s)
+                    rows, cols = rimg_shape(res)
+                    dt, _ = R.time_dynamic_idx(0, s, s, rows, cols)
+                    bd["hd_passes"] = bd.get("hd_passes", 0.0) + dt
+            # extractHighDynPointsViaKnnDiff + static projection on the true-size static maps
+            static = [self._subset(s, self.sizes["static_map_points"][s]) for s in (0, 1)]
+            for s in (0, 1):
+                R.knn_set_target(s, static[s], NUM_KNN, KNN_THR)               # kd-tree construction: fixed cost, untimed
+                dt, _ = R.time_knn_queries(s, False, self.cores)
+                bd["hd_knn"] = bd.get("hd_knn", 0.0) + dt
+                dt, _ = R.time_merge(s, "keyframe_scans_dynamic_")
+                bd["merges"] = bd.get("merges", 0.0) + dt
+                R.set_cloud("map_global_curr_", static[s], s)
+                bd["parse_static"] = bd.get("parse_static", 0.0) + R.time_parse_static(s)
+            # Step 2: kNN diff against the OTHER session's static map, then the ND / PD filter passes
+            for s in (0, 1):
+                R.knn_set_target(s, static[1 - s], NUM_KNN, KNN_THR)
+                dt, _ = R.time_knn_queries(s, True, self.cores)
+                bd["ld_knn"] = bd.get("ld_knn", 0.0) + dt
+                for name in ("scans_knn_diff_", "scans_knn_diff_", "scans_knn_coexist_"):   # constructGlobal{ND,PD}Map + the two merges of the viz block
+                    dt, _ = R.time_merge(s, name)
+                    bd["merges"] = bd.get("merges", 0.0) + dt
+            rows, cols = rimg_shape(2.5)
+            for n in self.sizes["nd_pass_map_points"]:
+                R.set_cloud("map_global_nd_", self._subset(0, n), 0)
+                dt, _ = R.time_dynamic_idx(1, 0, 1, rows, cols)                # ...ForND(central, query)
+                bd["nd_pd_passes"] = bd.get("nd_pd_passes", 0.0) + dt
+            for n in self.sizes["pd_pass_map_points"]:
+                R.set_cloud("map_global_pd_", self._subset(1, n), 1)
+                dt, _ = R.time_dynamic_idx(2, 1, 0, rows, cols)                # ...ForPD(query, central)
+                bd["nd_pd_passes"] = bd.get("nd_pd_passes", 0.0) + dt
+            R.close()
+        t_total = sum(bd.values())
+        self.last_breakdown = {k: round(v, 3) for k, v in bd.items()}
+        return t_total, 2 * S
+
+    def describe(self, seconds):
+        return (f"{self.S} keyframe(s) of each session per step (a different, evenly spread subset every step) through every per-keyframe loop of the "
+                f"step (9+9 selfRemovert passes, HD kNN, static projection, LD kNN, 3+3 ND/PD passes, keyframe merges) on maps of the TRUE per-pass size "
+                f"(stride subsets of the reference-built {self.sizes['map_points']} point maps of the full {self.kf}-keyframe pair; sizes from "
+                f"tests/golden/config2_pass_sizes.json); the reference's own member functions (oracle/_ref, its sources compiled unmodified behind "
+                f"third-party stand-ins, OpenMP on, {self.cores} threads); per-pass fixed costs (partition, voxelisation, kd-tree build, ~3 % of its step) "
+                f"left out in its favour; {seconds:.2f} s per sample; set-up {self.setup_s:.0f} s untimed")
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank):
     if rank != 0:
         return
-    cb = cpu_baseline_run(steps=args.steps, warmup=args.warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "keyframes/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (f64 transforms)", "data": "synthetic",
-            "config": {"workload": "configs[1] schedule on a bounded CPU sample (see cpu_baseline.sample)", "schedule": SCHEDULE,
-                       "num_knn": NUM_KNN, "knn_thr": KNN_THR, "keyframes_per_session": CPU_SAMPLE_KF},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": cb["value"], "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    sampler = ReferenceSampler(args.kf, S=args.ref_sample_kf)
+    times = []
+    for it in range(args.warmup + args.steps):
+        dt, nkf = sampler.step()
+        if it >= args.warmup:
+            times.append(dt)
+    dt = float(np.mean(times))
+    value = 2 * sampler.S / dt
+    cb = {"value": value, "unit": "keyframes/s", "cores": sampler.cores, "kind": "reference", "sample": sampler.describe(dt)}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "keyframes/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (f64 transforms)", "data": "synthetic", "config": workload_config(args.kf),
+            "cpu_baseline": cb, "sample_breakdown_s_last_step": sampler.last_breakdown,
+            "e2e": {"value": value, "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+# -----------------------------------------------------------------------------------------------------------------------------
+# Our arm
+# -----------------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--kf", type=int, default=KF_PER_GPU, help="keyframes per session per GPU")
+    ap.add_argument("--kf", type=int, default=KF_PER_SESSION, help="keyframes per session of the pair (whole job)")
+    ap.add_argument("--ref-sample-kf", type=int, default=1, help="reference arm: keyframes of each session per sample step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast-path", action="store_true")
+    ap.add_argument("--no-split", action="store_true", help="every rank owns a block of BOTH sessions (no session split)")
+    ap.add_argument("--no-e2e", action="store_true", help="diagnostic: skip the end-to-end arm")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: measure the sampler's own overhead")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank)
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3
 
@@ -220,40 +357,60 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: lt_mapper_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    comm = None
+    split = world >= 2 and world % 2 == 0 and not args.no_split
     if world > 1:
         with _QuietStdout(to_stderr=True):     # NCCL prints its version banner on stdout at communicator creation
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
             dist.barrier()
             torch.cuda.synchronize()
-        comm = removert.TorchDistComm()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    blocks = gen_block(rank, args.kf)
-    # pinned host copies: the e2e arm's H2D source
-    pinned = []
-    for d, inv in blocks:
-        t = torch.from_numpy(d.xyzi).pin_memory()
-        pinned.append((t, d.offsets, d.poses, inv))
-    h2d_bytes = sum(int(t.numel()) * 4 + o.nbytes + p.nbytes + ip.nbytes for t, o, p, ip in pinned)
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    R = removert.Removerter(device=local_rank, num_knn=NUM_KNN, knn_thr=KNN_THR, schedule=SCHEDULE, comm=comm,
-                            fast_path=not args.no_fast_path)
+    blocks = gen_blocks(rank, world, args.kf, split)
+    # pinned host copies: the e2e arm's H2D source
+    empty = (np.zeros((0, 4), np.float32), np.zeros(1, np.int64), np.zeros((0, 4, 4)), np.zeros((0, 4, 4)))
+    pinned, h2d_bytes = {}, 0
+    for s in (0, 1):
+        if blocks[s] is None:
+            pinned[s] = empty
+            continue
+        d, inv = blocks[s]
+        t = torch.from_numpy(d.xyzi).pin_memory()
+        pinned[s] = (t.numpy(), d.offsets, d.poses, inv)
+        h2d_bytes += int(t.numel()) * 4 + d.offsets.nbytes + d.poses.nbytes + inv.nbytes
+    pts_per_scan = float(np.mean([np.mean(np.diff(b[0].offsets)) for b in blocks.values() if b is not None]))
+
+    R = removert.Removerter(device=local_rank, num_knn=NUM_KNN, knn_thr=KNN_THR, schedule=schedule(), fast_path=not args.no_fast_path)
+    if world > 1:
+        ids = [removert.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        with _QuietStdout(to_stderr=True):
+            R.init_nccl(ids[0], rank, world, split_sessions=split)
 
     def load():
-        for s, (t, o, p, ip) in enumerate(pinned):
-            R.load_session(s, t.numpy(), o, p, ip)
+        for s in (0, 1):
+            R.load_session(s, *pinned[s])
 
+    stream = torch.cuda.ExternalStream(R.ctx.stream_handle())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def l2_flush():
+        with torch.cuda.stream(stream):   # on the LIBRARY's stream: ordered with the timed work
+            flush.zero_()
 
     # ---------------- device-resident arm: `value` ----------------
     load()
     R.run_step0()
-    n_map = [R.cloud_size("map_global_curr_", s) for s in (0, 1)]
+    n_map = [R.cloud_size("map_global_curr_", s) if R.owns(s) else None for s in (0, 1)]
     for _ in range(args.warmup):
         R.reset_to_step0(); R.run_step12()
     barrier()
@@ -266,10 +423,10 @@ def main():
     barrier()
     R.ctx.timer_start()
     for _ in range(args.steps):
-        flush.zero_()                 # L2 flush between timed iterations
+        l2_flush()                    # L2 flush between timed iterations
         R.reset_to_step0()
         R.run_step12()
-        for k in ("hd_remove", "hd_knn", "parse_static", "ld_knn", "ld_filter", "ld_merge_viz"):
+        for k in ("hd_remove", "hd_knn", "exchange", "parse_static", "ld_knn", "ld_filter", "ld_merge_viz"):
             stage_t[k] = stage_t.get(k, 0.0) + R.timing(k)
     ms_total = R.ctx.timer_stop()
     barrier()
@@ -279,48 +436,75 @@ def main():
     clocks = sampler.stop()
     prof = R.ctx.profile_get()
     passlog = R.log()
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    total_kf = 2 * args.kf * world
+    ms_step = max_over_ranks(ms_total) / args.steps
+    total_kf = 2 * args.kf
     value = total_kf / (ms_step * 1e-3)
 
-    # ---------------- end-to-end arm: host buffers -> host ND/PD maps ----------------
-    pinned_out = {}
-
-    def e2e_step():
-        load()                        # H2D from pinned memory, inside the timed region
-        R.run_step0()
-        R.run_step12()
-        n = 0
-        for name in LD_OUTPUTS:
-            try:
-                h = R.cloud_handle("saved:" + name)
-            except Exception:
-                continue
-            need = R.ctx.cloud_size(h)
-            if name not in pinned_out or len(pinned_out[name]) < need:      # pinned destination, grown on demand (warm-up)
-                pinned_out[name] = torch.empty((int(need * 1.25) + 1024, 4), dtype=torch.float32).pin_memory().numpy()
-            n += R.ctx.cloud_download(h, out=pinned_out[name]).nbytes      # D2H of the merged ND/PD / union maps
-        return n
-    e2e_iter_ms = []
-    for _ in range(max(3, args.warmup)):
-        t1 = time.perf_counter(); e2e_step(); e2e_iter_ms.append(round((time.perf_counter() - t1) * 1e3, 1))
-    barrier()
-    t0 = time.perf_counter()
-    R.ctx.timer_start()
-    d2h_bytes = 0
-    for _ in range(args.steps):
-        flush.zero_()
-        t1 = time.perf_counter(); d2h_bytes = e2e_step(); e2e_iter_ms.append(round((time.perf_counter() - t1) * 1e3, 1))
-    ms_e2e_dev = R.ctx.timer_stop()
-    barrier()
-    ms_e2e = max(ms_e2e_dev, (time.perf_counter() - t0) * 1e3)
-    t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+    # ---------------- digests of the step's outputs (parity across N: the driver's SCALE run must show identical ones) ----------------
+    mine = {}
+    for name in DIGEST_OUTPUTS:
+        try:
+            a = R.cloud("saved:" + name)
+        except Exception:  # noqa: BLE001 -- session-split: this rank does not hold that output
+            continue
+        mine[name] = [int(len(a)), hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()]
+    allv = [None] * world
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = total_kf / (float(t.item()) / args.steps * 1e-3)
+        dist.all_gather_object(allv, (mine, passlog))
+    else:
+        allv = [(mine, passlog)]
+    digests, replicas_identical, full_log = {}, True, {}
+    for m, lg in allv:
+        for k, v in m.items():
+            if k in digests and digests[k] != v:
+                replicas_identical = False
+            digests.setdefault(k, v)
+        for e in lg:
+            full_log.setdefault((e[0], e[1]), e)    # (what, n_map) -> entry; replicas log the same passes
+    passlog_all = [list(e) for e in full_log.values()]
+
+    # ---------------- end-to-end arm: host buffers -> host ND/PD maps ----------------
+    e2e = None
+    if not args.no_e2e:
+        pinned_out = {}
+        leader = (rank == 0) or (split and rank == world // 2)   # outputs are replicated inside a group: its first rank reads them back
+
+        def e2e_step():
+            load()                        # H2D from pinned memory, inside the timed region
+            R.run_step0()
+            R.run_step12()
+            n = 0
+            if leader:
+                for name in LD_OUTPUTS:
+                    try:
+                        h = R.cloud_handle("saved:" + name)
+                    except Exception:  # noqa: BLE001
+                        continue
+                    need = R.ctx.cloud_size(h)
+                    if name not in pinned_out or len(pinned_out[name]) < need:      # pinned destination, grown on demand (warm-up)
+                        pinned_out[name] = torch.empty((int(need * 1.25) + 1024, 4), dtype=torch.float32).pin_memory().numpy()
+                    n += R.ctx.cloud_download(h, out=pinned_out[name]).nbytes      # D2H of the merged ND/PD / union maps
+            return n
+        e2e_iter_ms = []
+        for _ in range(3):
+            t1 = time.perf_counter(); e2e_step(); e2e_iter_ms.append(round((time.perf_counter() - t1) * 1e3, 1))
+        barrier()
+        t0 = time.perf_counter()
+        R.ctx.timer_start()
+        d2h_bytes = 0
+        for _ in range(args.steps):
+            l2_flush()
+            t1 = time.perf_counter(); d2h_bytes = e2e_step(); e2e_iter_ms.append(round((time.perf_counter() - t1) * 1e3, 1))
+        ms_e2e_dev = R.ctx.timer_stop()
+        barrier()
+        ms_e2e = max_over_ranks(max(ms_e2e_dev, (time.perf_counter() - t0) * 1e3))
+        tb = torch.tensor([float(h2d_bytes), float(d2h_bytes)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        e2e = {"value": total_kf / (ms_e2e / args.steps * 1e-3), "unit": "keyframes/s", "h2d_bytes_per_step": int(tb[0].item()),
+               "d2h_bytes_per_step": int(tb[1].item()),
+               "region": "pinned host scans+poses -> H2D -> Step 0 + Step 1 + static projection + Step 2 -> D2H of the ND/PD/union maps (bytes summed over ranks)",
+               "iteration_ms_incl_warmup": e2e_iter_ms}
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -329,41 +513,46 @@ def main():
         k_bytes = prof[2] / max(prof[1], 1.0)
         achieved = (k_bytes / (k_us * 1e-6)) / 1e9 if k_us > 0 else 0.0
         traffic, traffic_note = None, "no ncu capture committed"
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                tj = json.load(f)
-            traffic = tj["dram_bytes_per_launch"]
-            traffic_note = (f"ncu --set full (profiles/r01_ncu_map_project_fast.md): dram__bytes_read+write per 32-keyframe launch on the N={tj['N']} map = "
-                            f"{tj['dram_bytes_per_launch'] / 1e6:.0f} MB vs {tj['algorithmic_bytes_per_launch'] / 1e6:.0f} MB algorithmic "
-                            "(the map tile is read once per 32 keyframes; images stay in L2) -> the kernel is instruction-issue bound, not DRAM bound")
-        roofline = {"bound": "hbm", "kernel": "map_project_fast_kernel<candidates> (remove/revert/PD passes; ND launches included)", "achieved": achieved,
+        for tp in ("r02_traffic.json", "r01_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", tp)
+            if os.path.exists(tp):
+                with open(tp) as f:
+                    tj = json.load(f)
+                traffic = tj["dram_bytes_per_launch"]
+                traffic_note = (f"ncu --set full ({tj.get('source', 'profiles/r01_ncu_map_project_fast.md')}): dram__bytes_read+write per 32-keyframe launch on the N={tj['N']} map = "
+                                f"{tj['dram_bytes_per_launch'] / 1e6:.0f} MB vs {tj['algorithmic_bytes_per_launch'] / 1e6:.0f} MB algorithmic "
+                                "(the map tile is read once per 32 keyframes; images stay in L2) -> the kernel is instruction-issue bound, not DRAM bound")
+                break
+        roofline = {"bound": "hbm", "kernel": "map_project_fast_kernel (remove/revert/ND/PD passes of rank 0)", "achieved": achieved,
                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                     "launches_timed": int(prof[1]), "avg_launch_us": k_us, "algorithmic_bytes_per_launch": k_bytes,
+                    "algorithmic_bytes_definition": "keyframes_in_launch * (12 N + N/8), N = map points (SURVEY.md section 8d, N_k = N: culled pairs count as processed)",
                     "point_projections_per_s": prof[3] / (prof[0] * 1e-6) if prof[0] > 0 else 0.0,
                     "kernel_share_of_step": (prof[0] / args.steps) / (ms_step * 1e3),
                     "parse_kernel": {"avg_launch_us": prof[4] / max(prof[5], 1.0), "achieved": (prof[6] / max(prof[4], 1e-9)) * 1e6 / 1e9}}
+        cfg = workload_config(args.kf)
         line = {"metric": METRIC, "value": value, "unit": "keyframes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (f64 transforms)", "data": "synthetic",
-                "config": {"workload": f"configs[1]: {args.kf}-keyframe two-session pair per GPU ({args.kf * world} keyframes/session total, "
-                                       f"keyframe-sharded), 64x1800 scans, 3 remove + 1 revert resolutions, kNN k=1 r=0.2m",
-                           "schedule": SCHEDULE, "num_knn": NUM_KNN, "knn_thr": KNN_THR, "points_per_scan": float(np.mean(np.diff(blocks[0][0].offsets))),
-                           "map_points": n_map, "timed_region": "Step 1 + static projection + Step 2 (Removerter.cpp:1665-1669), inputs resident in HBM",
-                           "l2": "256 MiB buffer written between timed iterations", "fast_path": not args.no_fast_path,
-                           "parallelism": f"keyframe-sharded x{world}, maps replicated"},
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 (f64 transforms)", "data": "synthetic", "config": cfg,
+                "run": {"points_per_scan": pts_per_scan, "map_points_rank0": n_map, "inputs": "resident in HBM (scans uploaded, Step 0 done) when the timed region starts",
+                        "l2": "256 MiB buffer written on the library's stream between timed iterations", "fast_path": not args.no_fast_path,
+                        "parallelism": (f"{world} ranks: " + ("session split (ranks < N/2 central, others query), " if split else "") +
+                                        "contiguous keyframe blocks per rank, maps replicated inside a group, native NCCL exchange points") if world > 1 else "1 GPU"},
                 "clocks": clocks, "gpu_launches": int(launches / args.steps),
-                "e2e": {"value": e2e_value, "unit": "keyframes/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                        "region": "pinned host scans+poses -> H2D -> Step 0 + Step 1 + static projection + Step 2 -> D2H of the ND/PD/union maps",
-                        "iteration_ms_incl_warmup": e2e_iter_ms},
                 "roofline": roofline,
-                "stages_ms_per_step": {k: v / args.steps * 1e3 for k, v in stage_t.items()},
-                "pass_log": passlog[:8]}
-        if comm is not None:
-            line["comm_hooks_rank0_total"] = {k: {"calls": v[0], "seconds": round(v[1], 4), "bytes": v[2]} for k, v in comm.stats.items()}
+                "stages_ms_per_step_rank0": {k: v / args.steps * 1e3 for k, v in stage_t.items()},
+                "output_digests": digests, "replicas_identical": replicas_identical,
+                "pass_log": passlog_all}
+        if e2e is not None:
+            line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline_run()
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            try:
+                rs = ReferenceSampler(args.kf, S=args.ref_sample_kf)
+                ts = [rs.step()[0] for _ in range(3)]
+                dt = float(np.mean(ts[1:]))
+                line["cpu_baseline"] = {"value": 2 * rs.S / dt, "unit": "keyframes/s", "cores": rs.cores, "kind": "reference", "sample": rs.describe(dt)}
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": "keyframes/s", "cores": 0, "kind": "reference", "sample": "unavailable: " + repr(e)}
         print(json.dumps(line), flush=True)
     R.close()
     if world > 1:

@@ -154,6 +154,29 @@ int ltr_knn_diff(ltr_ctx* ctx, ltr_scanset scans, ltr_poses poses, int32_t pose_
  * Session::removeWeakNDMapPointsHavingStrongNDInNear (Session.cpp:452-484). near = |avg| < thr, far = the rest. */
 int ltr_knn_split_cloud(ltr_ctx* ctx, ltr_cloud query, ltr_cloud target, int32_t k, float thr, ltr_cloud* out_near, ltr_cloud* out_far);
 
+/* ---- multi-GPU exchange points (NCCL, on the context's stream; libnccl is dlopen'ed at first use) ----------------
+ * The path shards by keyframe: every per-keyframe loop of the reference (Removerter.cpp:429-593, Session.cpp:348-427) runs on the
+ * rank owning the keyframe.  What crosses ranks: the OR of the per-pass dynamic flags (the reference's set union over scans,
+ * Removerter.cpp:588-590), clouds merged over all keyframes in keyframe order (utility.cpp:177-189), and whole maps handed from the
+ * ranks of one session to the ranks of the other.  Communicators are small int handles owned by the context. */
+int ltr_nccl_unique_id(uint8_t* id128);                       /* ncclGetUniqueId on the calling rank; share the 128 bytes with the others */
+int ltr_nccl_init(ltr_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world, int32_t* comm_out);
+int ltr_nccl_split(ltr_ctx* ctx, int32_t comm, int32_t color, int32_t key, int32_t* comm_out);   /* key = parent rank */
+int ltr_nccl_info(ltr_ctx* ctx, int32_t comm, int32_t* rank, int32_t* world);
+int ltr_nccl_destroy(ltr_ctx* ctx, int32_t comm);
+int ltr_nccl_version(int32_t* v);
+/* in-place ncclAllReduce(uint8, max) of the dynamic flags of `map` (identical maps on every rank of the communicator) */
+int ltr_nccl_allreduce_flags(ltr_ctx* ctx, int32_t comm, ltr_cloud map);
+/* out[i] = concatenation over ranks 0..world-1 of each rank's local[i]; one size exchange + ONE grouped send/recv for all clouds */
+int ltr_nccl_allgather_clouds(ltr_ctx* ctx, int32_t comm, int32_t count, const ltr_cloud* local, ltr_cloud* out);
+/* n_send clouds go to `peer`, n_recv clouds come from `peer` (the peer calls with the mirrored counts) */
+int ltr_nccl_exchange_clouds(ltr_ctx* ctx, int32_t comm, int32_t peer, int32_t n_send, const ltr_cloud* send, int32_t n_recv, ltr_cloud* recv);
+int ltr_nccl_allgather_i64(ltr_ctx* ctx, int32_t comm, const int64_t* local, int32_t count, int64_t* out /* world * count */);
+int ltr_nccl_max_f64(ltr_ctx* ctx, int32_t comm, double v, double* out);
+int ltr_nccl_barrier(ltr_ctx* ctx, int32_t comm);
+/* the cudaStream_t every kernel and collective of this context is enqueued on */
+void* ltr_stream_handle(ltr_ctx* ctx);
+
 /* ---- introspection for tests / profiling ----------------------------------------------------- */
 /* Evaluates the device restatement of cart2sph + pixel index (utility.cpp:38-56, 118-123) for n points. */
 int ltr_debug_pixel_index(ltr_ctx* ctx, const float* xyz /* n*3 */, int64_t n, int32_t rows, int32_t cols,
@@ -166,6 +189,13 @@ int ltr_debug_scan_rimg(ltr_ctx* ctx, ltr_scanset scans, int32_t kf, float res_a
  * margins4 (optional) = column margin a, column margin b (x r/rho), row margin, relative range margin. */
 int ltr_debug_fast_project(ltr_ctx* ctx, const float* xyz /* n*3 */, int64_t n, const double* inv_pose16, float res_alpha,
                            float* out8 /* n*8 */, float* margins4);
+/* Exhaustive sweep of the fast path's arctangent polynomials: which = 0 -> every float of [0, 1] through the azimuth polynomial,
+ * which = 1 -> every float of [0, 0.5] through the short elevation polynomial; returns max |poly(a) - atan(a)| (atan in double) and
+ * the argument where it occurs.  The error budget of the margins (project_fast.cuh) quotes these two numbers. */
+int ltr_debug_atan_sweep(ltr_ctx* ctx, int32_t which, double* max_abs_err, float* arg_at_max);
+/* margins8 of ltr_debug_margins: column margin a, column margin b (x r/rho), row margin, relative range margin, absolute range margin [m],
+ * el_direct flag, and the derived (un-inflated) column / row error bounds in pixels at r/rho = 1 */
+int ltr_debug_margins(ltr_ctx* ctx, float res_alpha, float* margins8);
 /* resetRimgSize (utility.cpp:222-236) */
 void ltr_reset_rimg_size(float vfov, float hfov, float alpha, int32_t* rows, int32_t* cols);
 /* Statistics of the last ltr_remove_pass / ltr_parse_projected: [0] (point, keyframe) pairs projected, [1] pairs settled by

@@ -65,6 +65,14 @@ void ltrh_destroy(ltrh_removerter* r);
 const char* ltrh_last_error(const ltrh_removerter* r);
 int ltrh_set_comm(ltrh_removerter* r, const ltr_comm* comm);
 ltr_ctx* ltrh_context(ltrh_removerter* r);
+/* Native multi-GPU transport (ltr_nccl_* of ltr_b200.h; NCCL on the context's stream, no host code in the loop).  id128 = the 128 bytes
+ * of ltr_nccl_unique_id() taken on one rank and shared with the others by the launcher.  split_sessions != 0 with an even world:
+ * ranks [0, world/2) own the keyframes of the central session, the others those of the query session (each a contiguous block,
+ * in rank order); Step 1 of the two sessions and the two halves of Step 2 then run concurrently and a map crosses over exactly
+ * where the reference reads the other session's member.  Otherwise every rank owns a block of BOTH sessions.
+ * ltrh_load_session on a rank that does not own the session is called with K = 0. */
+int ltrh_comm_init_nccl(ltrh_removerter* r, const uint8_t* id128, int32_t rank, int32_t world, int32_t split_sessions);
+int ltrh_owns_session(ltrh_removerter* r, int32_t sess);   /* 1 iff this rank holds keyframes of `sess` */
 
 /* sess: 0 = central, 1 = query.  Keyframes are this rank's block (all keyframes when world == 1). */
 int ltrh_load_session(ltrh_removerter* r, int32_t sess, const float* xyzi, const int64_t* offsets, const double* poses,

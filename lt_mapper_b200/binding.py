@@ -36,7 +36,9 @@ EXPORTS = [
     "ltr_scanset_free", "ltr_scanset_concat_per_keyframe", "ltr_scanset_flatten", "ltr_poses_upload", "ltr_poses_free",
     "ltr_preclean", "ltr_merge_scans_global", "ltr_voxel_centroid", "ltr_voxel_centroid_per_keyframe", "ltr_remove_pass",
     "ltr_flags_device_ptr", "ltr_flags_download", "ltr_flags_upload", "ltr_apply_partition", "ltr_parse_projected",
-    "ltr_knn_diff", "ltr_knn_split_cloud", "ltr_debug_pixel_index", "ltr_debug_scan_rimg", "ltr_debug_fast_project", "ltr_reset_rimg_size", "ltr_last_pass_stats", "ltr_profile_get", "ltr_profile_reset", "ltr_timer_start", "ltr_timer_stop", "ltr_trace_dump",
+    "ltr_knn_diff", "ltr_knn_split_cloud", "ltr_debug_pixel_index", "ltr_debug_scan_rimg", "ltr_debug_fast_project", "ltr_debug_atan_sweep", "ltr_debug_margins", "ltr_reset_rimg_size", "ltr_last_pass_stats", "ltr_profile_get", "ltr_profile_reset", "ltr_timer_start", "ltr_timer_stop", "ltr_trace_dump",
+    "ltr_nccl_unique_id", "ltr_nccl_init", "ltr_nccl_split", "ltr_nccl_info", "ltr_nccl_destroy", "ltr_nccl_version", "ltr_nccl_allreduce_flags",
+    "ltr_nccl_allgather_clouds", "ltr_nccl_exchange_clouds", "ltr_nccl_allgather_i64", "ltr_nccl_max_f64", "ltr_nccl_barrier", "ltr_stream_handle",
 ]
 
 
@@ -95,6 +97,8 @@ def lib():
     L.ltr_debug_pixel_index.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]
     L.ltr_debug_scan_rimg.argtypes = [vp, i32, i32, ctypes.c_float, vp]
     L.ltr_debug_fast_project.argtypes = [vp, vp, i64, vp, f32, vp, vp]
+    L.ltr_debug_atan_sweep.argtypes = [vp, i32, P(ctypes.c_double), P(f32)]
+    L.ltr_debug_margins.argtypes = [vp, f32, vp]
     L.ltr_reset_rimg_size.argtypes = [f32, f32, f32, P(i32), P(i32)]
     L.ltr_reset_rimg_size.restype = None
     L.ltr_last_pass_stats.argtypes = [vp, vp]
@@ -103,6 +107,20 @@ def lib():
     L.ltr_timer_start.argtypes = [vp]
     L.ltr_trace_dump.argtypes = [vp, i32]
     L.ltr_timer_stop.argtypes = [vp, P(ctypes.c_double)]
+    L.ltr_nccl_unique_id.argtypes = [vp]
+    L.ltr_nccl_init.argtypes = [vp, vp, i32, i32, P(i32)]
+    L.ltr_nccl_split.argtypes = [vp, i32, i32, i32, P(i32)]
+    L.ltr_nccl_info.argtypes = [vp, i32, P(i32), P(i32)]
+    L.ltr_nccl_destroy.argtypes = [vp, i32]
+    L.ltr_nccl_version.argtypes = [P(i32)]
+    L.ltr_nccl_allreduce_flags.argtypes = [vp, i32, i32]
+    L.ltr_nccl_allgather_clouds.argtypes = [vp, i32, i32, vp, vp]
+    L.ltr_nccl_exchange_clouds.argtypes = [vp, i32, i32, i32, vp, i32, vp]
+    L.ltr_nccl_allgather_i64.argtypes = [vp, i32, vp, i32, vp]
+    L.ltr_nccl_max_f64.argtypes = [vp, i32, ctypes.c_double, P(ctypes.c_double)]
+    L.ltr_nccl_barrier.argtypes = [vp, i32]
+    L.ltr_stream_handle.argtypes = [vp]
+    L.ltr_stream_handle.restype = vp
     _LIB = L
     return L
 
@@ -331,6 +349,17 @@ class Context:
         self._ck(lib().ltr_debug_fast_project(self._h, x.ctypes.data, len(x), ip.ctypes.data, res_alpha, out.ctypes.data, mg.ctypes.data))
         return out, mg
 
+    def debug_atan_sweep(self, which):
+        """(max |poly(a) - atan(a)|, argument) over EVERY float of [0, 1] (which = 0, azimuth polynomial) or [0, 0.5] (which = 1)."""
+        e, a = ctypes.c_double(), ctypes.c_float()
+        self._ck(lib().ltr_debug_atan_sweep(self._h, which, ctypes.byref(e), ctypes.byref(a)))
+        return e.value, a.value
+
+    def debug_margins(self, res_alpha):
+        m = np.zeros(8, np.float32)
+        self._ck(lib().ltr_debug_margins(self._h, res_alpha, m.ctypes.data))
+        return m
+
     def last_pass_stats(self):
         s = np.zeros(7, np.float64)
         self._ck(lib().ltr_last_pass_stats(self._h, s.ctypes.data))
@@ -369,3 +398,7 @@ class Context:
 
     def synchronize(self):
         self._ck(lib().ltr_synchronize(self._h))
+
+    def stream_handle(self):
+        """cudaStream_t (as int) every kernel and collective of this context runs on."""
+        return lib().ltr_stream_handle(self._h)

@@ -44,8 +44,8 @@ std::map<std::string, ltr_scanset*> Session::scanset_names() {
 }
 
 Removerter::Removerter(const ltrh_params& p) : P(p) {
-    central_sess_.sess_type_ = "Central";
-    query_sess_.sess_type_ = "Query";
+    central_sess_.sess_type_ = "Central"; central_sess_.id = 0;
+    query_sess_.sess_type_ = "Query"; query_sess_.id = 1;
     comm.rank = 0; comm.world = 1;
 }
 
@@ -128,7 +128,42 @@ int Removerter::save(const std::string& name, ltr_cloud c) {
     return LTR_OK;
 }
 
-int Removerter::reduce_flags(ltr_cloud map) {
+// ---------------------------------------------------------------------------------------------------------------
+// Parallel decomposition.  One process per GPU.
+//   * Keyframe sharding: the ranks that own a session hold contiguous keyframe blocks of it (scans + poses) in rank order; every
+//     per-keyframe loop of the reference runs on the owner.  Maps are replicated on those ranks; after a pass the per-rank flag
+//     arrays are OR-ed (reduce_flags) and every rank applies the same partition / voxelisation, so replicas stay bit-identical.
+//     Clouds merged over all keyframes are concatenated in rank == keyframe order (gather_clouds).
+//   * Session split (world even, split_sessions): ranks [0, world/2) own the central session, the others the query session.
+//     Step 1 of the two sessions (Removerter.cpp:1584 / 1587) and the two halves of Step 2 are independent, so the two groups
+//     run them concurrently and the replicated per-pass work (partition, voxelisation) is done once per group, not once per
+//     rank.  A map crosses groups exactly where the reference reads the other session's member: rank r hands it to rank
+//     r + world/2 (exchange_with_partner), one peer-to-peer transfer per rank pair.
+// Transport: the native NCCL entry points of libltr_b200.so (ltr_nccl_*), on the context's stream, no host code in the loop.
+// The legacy ltr_comm hooks remain for host-memory tests of the exchange logic (no session split).
+// ---------------------------------------------------------------------------------------------------------------
+int Removerter::comm_init_nccl(const uint8_t* id128, int rank_, int world_, int split_sessions) {
+    if (world_ < 1 || rank_ < 0 || rank_ >= world_) return fail(LTR_ERR_INVALID, "bad rank / world");
+    rank = rank_; world = world_;
+    split = split_sessions && world >= 2 && world % 2 == 0;
+    CK(ltr_nccl_init(ctx, id128, rank, world, &nccl_world));
+    if (split) {
+        int g;
+        CK(ltr_nccl_split(ctx, nccl_world, rank < world / 2 ? 0 : 1, rank, &g));
+        nccl_group[0] = nccl_group[1] = g;    // a rank only ever uses the group of the session it owns
+        group_world = world / 2;
+    } else {
+        nccl_group[0] = nccl_group[1] = nccl_world;
+        group_world = world;
+    }
+    return LTR_OK;
+}
+
+int Removerter::reduce_flags(ltr_cloud map, const Session& over) {
+    if (nccl_world >= 0) {
+        if (group_world <= 1) return LTR_OK;
+        return ltr_nccl_allreduce_flags(ctx, nccl_group[over.id], map) == LTR_OK ? LTR_OK : fail(LTR_ERR_CUDA, ltr_last_error(ctx));
+    }
     if (!has_comm || comm.world <= 1) return LTR_OK;
     uint8_t* p; int64_t n;
     CK(ltr_flags_device_ptr(ctx, map, &p, &n));
@@ -137,24 +172,42 @@ int Removerter::reduce_flags(ltr_cloud map) {
     return LTR_OK;
 }
 
-int Removerter::gather_cloud(ltr_cloud* cloud) {
+int Removerter::gather_clouds(const Session& over, int n, ltr_cloud** clouds) {
+    if (nccl_world >= 0) {
+        if (group_world <= 1) return LTR_OK;
+        ltr_cloud local[16] = {0}, out[16] = {0};
+        if (n > 16) return fail(LTR_ERR_INVALID, "too many clouds in one gather");
+        for (int i = 0; i < n; ++i) local[i] = *clouds[i];
+        CK(ltr_nccl_allgather_clouds(ctx, nccl_group[over.id], n, local, out));
+        for (int i = 0; i < n; ++i) CK(set(clouds[i], out[i]));
+        return LTR_OK;
+    }
     if (!has_comm || comm.world <= 1) return LTR_OK;
-    float *sx, *sy, *sz, *si; int64_t n;
-    CK(ltr_cloud_device_ptrs(ctx, *cloud, &sx, &sy, &sz, &si, &n));
-    std::vector<int64_t> counts((size_t)comm.world), displs((size_t)comm.world);
-    if (comm.allgather_i64(comm.user, n, counts.data()) != 0) return fail(LTR_ERR_CUDA, "allgather_i64 hook failed");
-    int64_t total = 0;
-    for (int r = 0; r < comm.world; ++r) { displs[r] = total; total += counts[r]; }
-    ltr_cloud g;
-    CK(ltr_cloud_alloc(ctx, total, &g));
-    float *dx, *dy, *dz, *di; int64_t m;
-    CK(ltr_cloud_device_ptrs(ctx, g, &dx, &dy, &dz, &di, &m));
-    CK(ltr_synchronize(ctx));
-    const float* src[4] = {sx, sy, sz, si};
-    float* dst[4] = {dx, dy, dz, di};
-    for (int c = 0; c < 4; ++c)
-        if (comm.allgatherv_f32(comm.user, src[c], n, dst[c], counts.data(), displs.data()) != 0) return fail(LTR_ERR_CUDA, "allgatherv_f32 hook failed");
-    return set(cloud, g);
+    for (int i = 0; i < n; ++i) {
+        ltr_cloud* cloud = clouds[i];
+        float *sx, *sy, *sz, *si; int64_t m;
+        CK(ltr_cloud_device_ptrs(ctx, *cloud, &sx, &sy, &sz, &si, &m));
+        std::vector<int64_t> counts((size_t)comm.world), displs((size_t)comm.world);
+        if (comm.allgather_i64(comm.user, m, counts.data()) != 0) return fail(LTR_ERR_CUDA, "allgather_i64 hook failed");
+        int64_t total = 0;
+        for (int r = 0; r < comm.world; ++r) { displs[r] = total; total += counts[r]; }
+        ltr_cloud g;
+        CK(ltr_cloud_alloc(ctx, total, &g));
+        float *dx, *dy, *dz, *di; int64_t mm;
+        CK(ltr_cloud_device_ptrs(ctx, g, &dx, &dy, &dz, &di, &mm));
+        CK(ltr_synchronize(ctx));
+        const float* src[4] = {sx, sy, sz, si};
+        float* dst[4] = {dx, dy, dz, di};
+        for (int c = 0; c < 4; ++c)
+            if (comm.allgatherv_f32(comm.user, src[c], m, dst[c], counts.data(), displs.data()) != 0) return fail(LTR_ERR_CUDA, "allgatherv_f32 hook failed");
+        CK(set(cloud, g));
+    }
+    return LTR_OK;
+}
+
+int Removerter::exchange_with_partner(int n_send, const ltr_cloud* send, int n_recv, ltr_cloud* recv) {
+    if (!split) return fail(LTR_ERR_INVALID, "exchange_with_partner outside session-split mode");
+    return ltr_nccl_exchange_clouds(ctx, nccl_world, partner(), n_send, send, n_recv, recv) == LTR_OK ? LTR_OK : fail(LTR_ERR_CUDA, ltr_last_error(ctx));
 }
 
 int Removerter::load_session(int sess, const float* xyzi, const int64_t* offsets, const double* poses, const double* inv_poses, int K) {
@@ -178,13 +231,14 @@ int Removerter::octreeDownsampling(ltr_cloud* cloud, float leaf) {
 int Removerter::mergeScansWithinGlobalCoordUtil(Session& s, ltr_scanset scans, ltr_cloud* out) {
     ltr_cloud m;
     CK(ltr_merge_scans_global(ctx, scans, s.keyframe_poses_, &m));
-    CK(gather_cloud(&m));  // keyframe order == rank order (contiguous keyframe blocks)
+    CK(gather_cloud(s, &m));  // keyframe order == rank order (contiguous keyframe blocks)
     *out = m;
     return LTR_OK;
 }
 
 int Removerter::precleaningKeyframes(float radius) {
     for (Session* s : {&central_sess_, &query_sess_}) {
+        if (!owns(*s)) continue;
         ltr_scanset c;
         CK(ltr_preclean(ctx, s->keyframe_scans_, radius, &c));
         CK(set(&s->keyframe_scans_, c, true));
@@ -203,8 +257,8 @@ int Removerter::makeGlobalMap(Session& s) {
     return LTR_OK;
 }
 int Removerter::makeGlobalMap() {
-    CK(makeGlobalMap(central_sess_));
-    CK(makeGlobalMap(query_sess_));
+    if (owns(central_sess_)) CK(makeGlobalMap(central_sess_));
+    if (owns(query_sess_)) CK(makeGlobalMap(query_sess_));
     return LTR_OK;
 }
 
@@ -215,7 +269,7 @@ int Removerter::partitionCurrentMapGeneric(ltr_cloud map, Session& source, ltr_s
     CK(ltr_cloud_size(ctx, map, &n_map));
     // n_dynamic is taken from the partition below (after the cross-rank flag union), so no count is requested here
     CK(ltr_remove_pass(ctx, map, scans, source.keyframe_poses_, 0, source.num_keyframes_, mode, res, 0.1f, 0, nullptr));
-    CK(reduce_flags(map));
+    CK(reduce_flags(map, source));
     CK(ltr_apply_partition(ctx, map, stat, dyn));
     int64_t n_dyn = 0;
     CK(ltr_cloud_size(ctx, *dyn, &n_dyn));
@@ -303,24 +357,31 @@ int Removerter::extractHighDynPointsViaKnnDiff(Session& s, ltr_cloud target_map)
 }
 
 int Removerter::removeHighDynamicPoints() {
+    Session& C = central_sess_;
+    Session& Q = query_sess_;
     {
         StageTimer t(*this, "hd_remove");
-        CK(selfRemovert(central_sess_));  // shipped schedule: removeOnce(central, central, 2.5) (:1584)
-        CK(selfRemovert(query_sess_));    // shipped schedule: removeOnce(query, query, 2.5)     (:1587)
+        if (owns(C)) CK(selfRemovert(C));  // shipped schedule: removeOnce(central, central, 2.5) (:1584)
+        if (owns(Q)) CK(selfRemovert(Q));  // shipped schedule: removeOnce(query, query, 2.5)     (:1587)
     }
     if (P.extract_high_dyn_knn) {
         StageTimer t(*this, "hd_knn");
-        CK(extractHighDynPointsViaKnnDiff(central_sess_, central_sess_.map_global_curr_static_));  // :1591
-        CK(extractHighDynPointsViaKnnDiff(query_sess_, query_sess_.map_global_curr_static_));      // :1592
-        ltr_cloud c, q;
-        CK(mergeScansWithinGlobalCoordUtil(central_sess_, central_sess_.keyframe_scans_dynamic_, &c));  // :1594
-        CK(mergeScansWithinGlobalCoordUtil(query_sess_, query_sess_.keyframe_scans_dynamic_, &q));      // :1595
-        CK(octreeDownsampling(&c, 0.05f));  // :1597
-        CK(octreeDownsampling(&q, 0.05f));  // :1598
-        CK(save("central_sess_high_dyn", c));  // :1600
-        CK(save("query_sess_high_dyn", q));    // :1601
-        CK(ltr_cloud_free(ctx, c));
-        CK(ltr_cloud_free(ctx, q));
+        if (owns(C)) CK(extractHighDynPointsViaKnnDiff(C, C.map_global_curr_static_));  // :1591
+        if (owns(Q)) CK(extractHighDynPointsViaKnnDiff(Q, Q.map_global_curr_static_));  // :1592
+        ltr_cloud c = -1, q = -1;
+        if (owns(C)) CK(mergeScansWithinGlobalCoordUtil(C, C.keyframe_scans_dynamic_, &c));  // :1594
+        if (owns(Q)) CK(mergeScansWithinGlobalCoordUtil(Q, Q.keyframe_scans_dynamic_, &q));  // :1595
+        if (owns(C)) { CK(octreeDownsampling(&c, 0.05f)); CK(save("central_sess_high_dyn", c)); CK(ltr_cloud_free(ctx, c)); }  // :1597, :1600
+        if (owns(Q)) { CK(octreeDownsampling(&q, 0.05f)); CK(save("query_sess_high_dyn", q)); CK(ltr_cloud_free(ctx, q)); }    // :1598, :1601
+    }
+    if (split) {
+        // Step 2 reads the OTHER session's static map (Removerter.cpp:1416, 1418): hand mine to my partner, take theirs
+        StageTimer t(*this, "exchange");
+        Session& mine = owns(C) ? C : Q;
+        Session& other = owns(C) ? Q : C;
+        ltr_cloud got = -1;
+        CK(exchange_with_partner(1, &mine.map_global_curr_static_, 1, &got));
+        CK(set(&other.map_global_curr_static_, got));
     }
     return LTR_OK;
 }
@@ -333,8 +394,8 @@ int Removerter::parseScansViaProjection(Session& s, ltr_cloud map, ltr_scanset* 
 
 int Removerter::parseStaticScansViaProjection() {
     StageTimer t(*this, "parse_static");
-    CK(parseScansViaProjection(central_sess_, central_sess_.map_global_curr_, &central_sess_.keyframe_scans_static_projected_));  // Session.cpp:305-308
-    CK(parseScansViaProjection(query_sess_, query_sess_.map_global_curr_, &query_sess_.keyframe_scans_static_projected_));
+    if (owns(central_sess_)) CK(parseScansViaProjection(central_sess_, central_sess_.map_global_curr_, &central_sess_.keyframe_scans_static_projected_));  // Session.cpp:305-308
+    if (owns(query_sess_)) CK(parseScansViaProjection(query_sess_, query_sess_.map_global_curr_, &query_sess_.keyframe_scans_static_projected_));
     return LTR_OK;
 }
 
@@ -384,42 +445,81 @@ int Removerter::filterStrongPD(Session& t, Session& s) {
     return LTR_OK;
 }
 
+// In session-split mode a member lives on the ranks that run the loops producing it:
+//   owners of the query keyframes:   filterStrongND (it projects into QUERY keyframes, :1403-1411) -> central map_global_nd_{,strong_,weak_},
+//                                    union_map_queryside, pd_map, strong_nd_map, weak_nd_map
+//   owners of the central keyframes: filterStrongPD (it projects into CENTRAL keyframes, :1395-1401) -> query map_global_pd_{,strong_,weak_} and the
+//                                    central copies (:1434-1436), union_map_centralside, nd_map, strong_pd_map, weak_pd_map
 int Removerter::detectLowDynamicPoints() {
     Session& C = central_sess_;
     Session& Q = query_sess_;
     {
         StageTimer t(*this, "ld_knn");
-        CK(extractLowDynPointsViaKnnDiff(C, Q.map_global_curr_static_));  // :1416
-        CK(extractLowDynPointsViaKnnDiff(Q, C.map_global_curr_static_));  // :1418
+        if (owns(C)) CK(extractLowDynPointsViaKnnDiff(C, Q.map_global_curr_static_));  // :1416
+        if (owns(Q)) CK(extractLowDynPointsViaKnnDiff(Q, C.map_global_curr_static_));  // :1418
     }
     {
         StageTimer t(*this, "ld_filter");
-        CK(constructGlobalNDMap(C));                        // :1421
-        if (C.map_global_nd_weak_ < 0) CK(assign(&C.map_global_nd_weak_, -1));
-        CK(filterStrongND(C, Q));                           // :1423
-        CK(removeWeakNDMapPointsHavingStrongNDInNear(C));   // :1424
-        CK(constructGlobalPDMap(Q));                        // :1427
-        if (Q.map_global_pd_weak_ < 0) CK(assign(&Q.map_global_pd_weak_, -1));
-        CK(filterStrongPD(Q, C));                           // :1429
-        // revertStrongPDMapPointsHavingWeakPDInNear: empty TODO in the reference (Session.cpp:447-450)
-        CK(assign(&C.map_global_pd_, Q.map_global_pd_));                  // :1434
-        CK(assign(&C.map_global_pd_orig_, Q.map_global_pd_orig_));        // :1435
-        CK(assign(&C.map_global_pd_strong_, Q.map_global_pd_strong_));    // :1436
+        if (owns(C)) CK(constructGlobalNDMap(C));           // :1421
+        if (split) {
+            // :1427 is independent of :1421-1424, so the query side builds its PD map now and the two maps cross over
+            if (owns(Q)) CK(constructGlobalPDMap(Q));
+            ltr_cloud got = -1;
+            // the sender drops its copy: from here on the member lives only where its filter passes run
+            if (owns(C)) {
+                CK(exchange_with_partner(1, &C.map_global_nd_, 1, &got));
+                CK(set(&C.map_global_nd_, -1));
+                CK(set(&Q.map_global_pd_, got)); CK(assign(&Q.map_global_pd_orig_, Q.map_global_pd_));   // Session.cpp:444
+            } else {
+                CK(exchange_with_partner(1, &Q.map_global_pd_, 1, &got));
+                CK(set(&Q.map_global_pd_, -1)); CK(set(&Q.map_global_pd_orig_, -1));
+                CK(set(&C.map_global_nd_, got));
+            }
+        }
+        if (owns(Q)) {
+            if (C.map_global_nd_weak_ < 0) CK(assign(&C.map_global_nd_weak_, -1));
+            CK(filterStrongND(C, Q));                           // :1423
+            CK(removeWeakNDMapPointsHavingStrongNDInNear(C));   // :1424
+        }
+        if (!split) CK(constructGlobalPDMap(Q));                // :1427
+        if (owns(C)) {
+            if (Q.map_global_pd_weak_ < 0) CK(assign(&Q.map_global_pd_weak_, -1));
+            CK(filterStrongPD(Q, C));                           // :1429
+            // revertStrongPDMapPointsHavingWeakPDInNear: empty TODO in the reference (Session.cpp:447-450)
+            CK(assign(&C.map_global_pd_, Q.map_global_pd_));                  // :1434
+            CK(assign(&C.map_global_pd_orig_, Q.map_global_pd_orig_));        // :1435
+            CK(assign(&C.map_global_pd_strong_, Q.map_global_pd_strong_));    // :1436
+        }
     }
     {
-        // always-on "save merged maps for visual debug" block (:1442-1480) including its in-place re-downsampling
+        // always-on "save merged maps for visual debug" block (:1442-1480) including its in-place re-downsampling.
+        // The four merges of a rank are gathered with ONE size exchange and ONE grouped transfer.
         StageTimer t(*this, "ld_merge_viz");
-        ltr_cloud m;
-        CK(mergeScansWithinGlobalCoordUtil(Q, Q.scans_knn_coexist_, &m)); CK(octreeDownsampling(&m, 0.05f)); CK(save("union_map_queryside", m)); CK(ltr_cloud_free(ctx, m));
-        CK(mergeScansWithinGlobalCoordUtil(C, C.scans_knn_coexist_, &m)); CK(octreeDownsampling(&m, 0.05f)); CK(save("union_map_centralside", m)); CK(ltr_cloud_free(ctx, m));
-        CK(mergeScansWithinGlobalCoordUtil(Q, Q.scans_knn_diff_, &m)); CK(octreeDownsampling(&m, 0.05f)); CK(save("pd_map", m)); CK(ltr_cloud_free(ctx, m));
-        CK(mergeScansWithinGlobalCoordUtil(C, C.scans_knn_diff_, &m)); CK(octreeDownsampling(&m, 0.05f)); CK(save("nd_map", m)); CK(ltr_cloud_free(ctx, m));
-        int64_t n = 0;
-        CK(ltr_cloud_size(ctx, C.map_global_nd_strong_, &n));
-        if (n != 0) { CK(octreeDownsampling(&C.map_global_nd_strong_, 0.05f)); CK(save("strong_nd_map", C.map_global_nd_strong_)); }
-        CK(octreeDownsampling(&C.map_global_nd_weak_, 0.05f)); CK(save("weak_nd_map", C.map_global_nd_weak_));
-        CK(octreeDownsampling(&Q.map_global_pd_strong_, 0.05f)); CK(save("strong_pd_map", Q.map_global_pd_strong_));
-        CK(octreeDownsampling(&Q.map_global_pd_weak_, 0.05f)); CK(save("weak_pd_map", Q.map_global_pd_weak_));
+        ltr_cloud qco = -1, cco = -1, qdi = -1, cdi = -1;
+        if (owns(Q)) { CK(ltr_merge_scans_global(ctx, Q.scans_knn_coexist_, Q.keyframe_poses_, &qco)); CK(ltr_merge_scans_global(ctx, Q.scans_knn_diff_, Q.keyframe_poses_, &qdi)); }
+        if (owns(C)) { CK(ltr_merge_scans_global(ctx, C.scans_knn_coexist_, C.keyframe_poses_, &cco)); CK(ltr_merge_scans_global(ctx, C.scans_knn_diff_, C.keyframe_poses_, &cdi)); }
+        if (split) {
+            ltr_cloud* two_q[2] = {&qco, &qdi};
+            ltr_cloud* two_c[2] = {&cco, &cdi};
+            if (owns(Q)) CK(gather_clouds(Q, 2, two_q)); else CK(gather_clouds(C, 2, two_c));
+        } else {
+            ltr_cloud* four[4] = {&qco, &cco, &qdi, &cdi};
+            CK(gather_clouds(C, 4, four));
+        }
+        if (owns(Q)) { CK(octreeDownsampling(&qco, 0.05f)); CK(save("union_map_queryside", qco)); CK(ltr_cloud_free(ctx, qco)); }     // :1443-1446
+        if (owns(C)) { CK(octreeDownsampling(&cco, 0.05f)); CK(save("union_map_centralside", cco)); CK(ltr_cloud_free(ctx, cco)); }   // :1448-1451
+        if (owns(Q)) { CK(octreeDownsampling(&qdi, 0.05f)); CK(save("pd_map", qdi)); CK(ltr_cloud_free(ctx, qdi)); }                  // :1453-1456
+        if (owns(C)) { CK(octreeDownsampling(&cdi, 0.05f)); CK(save("nd_map", cdi)); CK(ltr_cloud_free(ctx, cdi)); }                  // :1458-1461
+        if (owns(Q)) {   // the ND members live where filterStrongND ran
+            int64_t n = 0;
+            CK(ltr_cloud_size(ctx, C.map_global_nd_strong_, &n));
+            if (n != 0) { CK(octreeDownsampling(&C.map_global_nd_strong_, 0.05f)); CK(save("strong_nd_map", C.map_global_nd_strong_)); }   // :1463-1468
+            CK(octreeDownsampling(&C.map_global_nd_weak_, 0.05f)); CK(save("weak_nd_map", C.map_global_nd_weak_));                          // :1470-1472
+        }
+        if (owns(C)) {   // the PD members live where filterStrongPD ran
+            CK(octreeDownsampling(&Q.map_global_pd_strong_, 0.05f)); CK(save("strong_pd_map", Q.map_global_pd_strong_));   // :1474-1476
+            CK(octreeDownsampling(&Q.map_global_pd_weak_, 0.05f)); CK(save("weak_pd_map", Q.map_global_pd_weak_));         // :1478-1480
+        }
     }
     return LTR_OK;
 }
@@ -427,8 +527,22 @@ int Removerter::detectLowDynamicPoints() {
 int Removerter::updateCurrentMap() {
     Session& C = central_sess_;
     Session& Q = query_sess_;
-    ltr_cloud uq, uc, upd = -1, strong = -1;
-    CK(mergeScansWithinGlobalCoordUtil(Q, Q.scans_knn_coexist_, &uq)); CK(octreeDownsampling(&uq, 0.05f));  // :1489-1490
+    ltr_cloud uq = -1, uc = -1, upd = -1, strong = -1;
+    if (owns(Q)) { CK(mergeScansWithinGlobalCoordUtil(Q, Q.scans_knn_coexist_, &uq)); CK(octreeDownsampling(&uq, 0.05f)); }  // :1489-1490
+    if (split) {
+        // Step 3 runs on the owners of the central keyframes; the query side hands over what it holds of the central session
+        if (owns(Q)) {
+            const ltr_cloud send[3] = {uq, C.map_global_nd_weak_, C.map_global_nd_strong_};
+            CK(exchange_with_partner(3, send, 0, nullptr));
+            CK(ltr_cloud_free(ctx, uq));
+            return LTR_OK;
+        }
+        ltr_cloud got[3] = {-1, -1, -1};
+        CK(exchange_with_partner(0, nullptr, 3, got));
+        uq = got[0];
+        CK(set(&C.map_global_nd_weak_, got[1]));
+        CK(set(&C.map_global_nd_strong_, got[2]));
+    }
     CK(mergeScansWithinGlobalCoordUtil(C, C.scans_knn_coexist_, &uc)); CK(octreeDownsampling(&uc, 0.05f));  // :1492-1493
     CK(assign(&upd, uq));                       // :1495
     CK(append(&upd, uc));                       // :1496
@@ -447,6 +561,7 @@ int Removerter::updateCurrentMap() {
 
 int Removerter::parseUpdatedStaticScansViaProjection() {
     Session& C = central_sess_;
+    if (!owns(C)) return LTR_OK;
     CK(parseScansViaProjection(C, C.map_global_updated_, &C.keyframe_scans_updated_));
     CK(parseScansViaProjection(C, C.map_global_updated_strong_, &C.keyframe_scans_updated_strong_));
     return LTR_OK;
@@ -454,6 +569,7 @@ int Removerter::parseUpdatedStaticScansViaProjection() {
 
 int Removerter::parseLDScansViaProjection() {
     Session& C = central_sess_;
+    if (!owns(C)) return LTR_OK;
     CK(parseScansViaProjection(C, C.map_global_pd_orig_, &C.keyframe_scans_pd_));
     CK(parseScansViaProjection(C, C.map_global_pd_strong_, &C.keyframe_scans_strong_pd_));
     CK(parseScansViaProjection(C, C.map_global_nd_weak_, &C.keyframe_scans_weak_nd_));
@@ -463,6 +579,7 @@ int Removerter::parseLDScansViaProjection() {
 
 int Removerter::updateScansScanwise() {
     Session& C = central_sess_;
+    if (!owns(C)) return LTR_OK;
     ltr_scanset a, b, v;
     CK(ltr_scanset_concat_per_keyframe(ctx, C.keyframe_scans_updated_, C.keyframe_scans_weak_nd_, &a));  // Session.cpp:367-370
     CK(ltr_scanset_concat_per_keyframe(ctx, a, C.keyframe_scans_pd_, &b));                               // Session.cpp:371
@@ -497,6 +614,10 @@ int Removerter::run_step3() {
 int Removerter::reset_to_step0() {
     for (Session* s : {&central_sess_, &query_sess_}) {
         auto it = saved.find("OriginalNoisy" + s->sess_type_ + "MapGlobal");
+        if (!owns(*s)) {   // session-split: everything held of the other session was derived after Step 0
+            for (auto& kv : s->cloud_names()) if (*kv.second >= 0) { CK(ltr_cloud_free(ctx, *kv.second)); *kv.second = -1; }
+            continue;
+        }
         if (it == saved.end()) return fail(LTR_ERR_INVALID, "reset_to_step0: Step 0 has not run");
         for (auto& kv : s->cloud_names()) {
             if (kv.first == "map_global_orig_" || kv.first == "map_global_curr_") continue;
@@ -526,12 +647,12 @@ int Removerter::reset_to_step0() {
 // derived from the finished pair, and the query session, is released; the caller loads the next query and runs Steps 0-3 again.
 int Removerter::cascade_promote_updated() {
     Session& C = central_sess_;
-    if (C.keyframe_scans_updated_ < 0) return fail(LTR_ERR_INVALID, "cascade: Step 3 has not run (no keyframe_scans_updated_)");
+    if (owns(C) && C.keyframe_scans_updated_ < 0) return fail(LTR_ERR_INVALID, "cascade: Step 3 has not run (no keyframe_scans_updated_)");
     int32_t K = 0; int64_t total = 0;
-    CK(ltr_scanset_info(ctx, C.keyframe_scans_updated_, &K, &total));
+    if (owns(C)) CK(ltr_scanset_info(ctx, C.keyframe_scans_updated_, &K, &total));
     std::vector<float> xyzi((size_t)std::max<int64_t>(total, 1) * 4);
     std::vector<int64_t> off((size_t)K + 1, 0);
-    CK(ltr_scanset_download(ctx, C.keyframe_scans_updated_, xyzi.data(), total, off.data()));
+    if (owns(C)) CK(ltr_scanset_download(ctx, C.keyframe_scans_updated_, xyzi.data(), total, off.data()));
     // host-side load-time VoxelGrid, keyframes are independent (the reference's loadKeyframes loop is serial; the per-scan
     // arithmetic and its std::sort are unchanged, only different scans run on different threads)
     std::vector<HostCloud> grids((size_t)K);
@@ -559,10 +680,12 @@ int Removerter::cascade_promote_updated() {
     saved.clear();
     if (query_sess_.keyframe_poses_ >= 0) { CK(ltr_poses_free(ctx, query_sess_.keyframe_poses_)); query_sess_.keyframe_poses_ = -1; }
     query_sess_.num_keyframes_ = 0;
-    ltr_scanset ss;
-    if (out.empty()) out.resize(4);
-    CK(ltr_scanset_upload(ctx, out.data(), out_off.data(), K, &ss));
-    C.keyframe_scans_ = ss;
+    if (owns(C)) {
+        ltr_scanset ss;
+        if (out.empty()) out.resize(4);
+        CK(ltr_scanset_upload(ctx, out.data(), out_off.data(), K, &ss));
+        C.keyframe_scans_ = ss;
+    }
     log.clear();
     timing.clear();
     return LTR_OK;
@@ -619,6 +742,12 @@ int ltrh_set_comm(ltrh_removerter* r, const ltr_comm* comm) {
     return LTR_OK;
 }
 ltr_ctx* ltrh_context(ltrh_removerter* r) { return r ? r->R->ctx : nullptr; }
+int ltrh_comm_init_nccl(ltrh_removerter* r, const uint8_t* id128, int32_t rank, int32_t world, int32_t split_sessions) {
+    if (!r || !id128) return LTR_ERR_INVALID;
+    r->R->err.clear();
+    return r->R->comm_init_nccl(id128, rank, world, split_sessions);
+}
+int ltrh_owns_session(ltrh_removerter* r, int32_t sess) { return r && r->R->owns(sess == 0 ? r->R->central_sess_ : r->R->query_sess_) ? 1 : 0; }
 
 int ltrh_load_session(ltrh_removerter* r, int32_t sess, const float* xyzi, const int64_t* offsets, const double* poses, const double* inv_poses, int32_t K) {
     if (!r || (sess != 0 && sess != 1)) return LTR_ERR_INVALID;

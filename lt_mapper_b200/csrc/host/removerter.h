@@ -20,6 +20,7 @@ class Session {
 public:
     static constexpr float kReprojectionAlpha = 3.0f;  // Session.h:13
     std::string sess_type_;
+    int id = 0;                                        // 0 = central, 1 = query
     int num_keyframes_ = 0;                            // this rank's keyframes
     ltr_poses keyframe_poses_ = -1;                    // keyframe_poses_ + keyframe_inverse_poses_ (Session.h:36-37)
     // per-keyframe clouds (Session.h:40-56)
@@ -85,14 +86,26 @@ public:
     int assign(ltr_cloud* dst, ltr_cloud src);     // "*dst = *src" (deep copy)
     int append(ltr_cloud* dst, ltr_cloud src);     // "*dst += *src"
     int save(const std::string& name, ltr_cloud c);  // stands for pcl::io::savePCDFileBinary: keeps a device copy by name
-    int reduce_flags(ltr_cloud map);               // comm hook 1
-    int gather_cloud(ltr_cloud* cloud);            // comm hook 2+3: replaces a rank-local cloud by the rank-ordered concatenation
+    // ---- multi-GPU (see "Parallel decomposition" in removerter.cpp) ----
+    int comm_init_nccl(const uint8_t* id128, int rank, int world, int split_sessions);   // native NCCL transport (ltr_nccl_*)
+    bool owns(const Session& s) const { return !split || (rank < world / 2) == (s.id == 0); }
+    bool multi() const { return world > 1; }
+    int partner() const { return (rank + world / 2) % world; }
+    int reduce_flags(ltr_cloud map, const Session& over);               // OR of the dynamic flags over the ranks that own `over`'s keyframes
+    int gather_clouds(const Session& over, int n, ltr_cloud** clouds);  // each *clouds[i] <- rank-ordered concatenation over those ranks
+    int gather_cloud(const Session& over, ltr_cloud* cloud) { ltr_cloud* one[1] = {cloud}; return gather_clouds(over, 1, one); }
+    int exchange_with_partner(int n_send, const ltr_cloud* send, int n_recv, ltr_cloud* recv);   // split mode only
     int fail(int code, const std::string& msg);
 
     ltrh_params P;
     ltr_ctx* ctx = nullptr;
-    ltr_comm comm{};
+    ltr_comm comm{};          // legacy caller-supplied hooks (host-memory tests); superseded by the native transport when nccl_world >= 0
     bool has_comm = false;
+    int rank = 0, world = 1;
+    bool split = false;       // session-split: ranks [0, world/2) own the central keyframes, the others the query keyframes
+    int nccl_world = -1;      // ltr_nccl communicator handles: everyone, ...
+    int nccl_group[2] = {-1, -1};   // ... and the ranks that own session s
+    int group_world = 1;
     Session central_sess_, query_sess_;
     std::map<std::string, ltr_cloud> saved;
     std::map<std::string, double> timing;

@@ -110,6 +110,23 @@ __device__ __forceinline__ uint8_t knn_label(const Grid& g, const uint32_t* __re
     return (fabsf(avg) < thr) ? 0 : 1;
 }
 
+// Target with fewer than k points (1 <= n < k <= kMaxK): PCL's nearestKSearch returns all n of them (ascending), the reference still
+// divides their sum by k (Session.cpp:470-471, 592-594).  Brute force over the n points held in shared memory.
+__device__ __forceinline__ uint8_t knn_label_small(const float4* __restrict__ s_t, int n, float qx, float qy, float qz, int k, float thr) {
+    float d[kMaxK];
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) d[j] = __int_as_float(0x7f800000);
+    for (int p = 0; p < n; ++p) {
+        float v = l2_simple(qx, qy, qz, s_t[p].x, s_t[p].y, s_t[p].z);
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j) if (v < d[j]) { const float t = d[j]; d[j] = v; v = t; }   // ascending insertion
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) if (j < n) sum = da(sum, (double)d[j]);
+    return (fabsf(fd(__double2float_rn(sum), (float)k)) < thr) ? 0 : 1;
+}
+
 __device__ __forceinline__ uint8_t knn_label_dispatch(const Grid& g, const uint32_t* __restrict__ cell_start, const float4* __restrict__ sorted,
                                                       float qx, float qy, float qz, int k, float thr) {
     switch (k) {
@@ -126,7 +143,10 @@ __global__ void __launch_bounds__(128) knn_scan_label_kernel(PtrView scans, cons
                                                              int pose_offset, const double* __restrict__ ext, int ext_identity, int order, Grid g,
                                                              const uint32_t* __restrict__ cell_start, const float4* __restrict__ sorted, int k,
                                                              float thr, uint8_t* __restrict__ label, float* __restrict__ gx, float* __restrict__ gy,
-                                                             float* __restrict__ gz) {
+                                                             float* __restrict__ gz, PtrView small_target) {
+    __shared__ float4 s_t[kMaxK];
+    if (small_target.n > 0 && threadIdx.x < small_target.n) s_t[threadIdx.x] = make_float4(small_target.x[threadIdx.x], small_target.y[threadIdx.x], small_target.z[threadIdx.x], 0.0f);
+    if (small_target.n > 0) __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= scans.n) return;
     int lo = 0, hi = K;
@@ -135,7 +155,7 @@ __global__ void __launch_bounds__(128) knn_scan_label_kernel(PtrView scans, cons
     if (!ext_identity) transform_point(ext, order, x, y, z, &x, &y, &z);                              // utility.cpp:164 with base2lidar (as written)
     transform_point(poses + (size_t)(pose_offset + lo) * 24 + 12, order, x, y, z, &x, &y, &z);        // utility.cpp:165
     gx[i] = x; gy[i] = y; gz[i] = z;
-    label[i] = knn_label_dispatch(g, cell_start, sorted, x, y, z, k, thr);
+    label[i] = small_target.n > 0 ? knn_label_small(s_t, (int)small_target.n, x, y, z, k, thr) : knn_label_dispatch(g, cell_start, sorted, x, y, z, k, thr);
 }
 
 // global2local of the partitioned points (Session.cpp:603-604)
@@ -154,10 +174,15 @@ __global__ void __launch_bounds__(256) knn_relocalise_kernel(const float* __rest
 }
 
 __global__ void __launch_bounds__(128) knn_cloud_label_kernel(PtrView q, Grid g, const uint32_t* __restrict__ cell_start,
-                                                              const float4* __restrict__ sorted, int k, float thr, uint8_t* __restrict__ label) {
+                                                              const float4* __restrict__ sorted, int k, float thr, uint8_t* __restrict__ label,
+                                                              PtrView small_target) {
+    __shared__ float4 s_t[kMaxK];
+    if (small_target.n > 0 && threadIdx.x < small_target.n) s_t[threadIdx.x] = make_float4(small_target.x[threadIdx.x], small_target.y[threadIdx.x], small_target.z[threadIdx.x], 0.0f);
+    if (small_target.n > 0) __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q.n) return;
-    label[i] = knn_label_dispatch(g, cell_start, sorted, q.x[i], q.y[i], q.z[i], k, thr);
+    label[i] = small_target.n > 0 ? knn_label_small(s_t, (int)small_target.n, q.x[i], q.y[i], q.z[i], k, thr)
+                                  : knn_label_dispatch(g, cell_start, sorted, q.x[i], q.y[i], q.z[i], k, thr);
 }
 
 struct GridBuf {
@@ -227,7 +252,8 @@ int ltr_knn_diff(ltr_ctx* ctx, ltr_scanset scans_h, ltr_poses poses_h, int32_t p
     if (k < 1 || k > kMaxK) return fail(ctx, LTR_ERR_UNSUPPORTED, "k = %d outside [1, %d]", k, kMaxK);
     if (!(thr > 0.0f)) return fail(ctx, LTR_ERR_INVALID, "threshold must be positive");
     if (pose_offset < 0 || pose_offset + sp->K > pp->K) return fail(ctx, LTR_ERR_INVALID, "pose range [%d,%d) outside [0,%d)", pose_offset, pose_offset + sp->K, pp->K);
-    if (tp->n < k) return fail(ctx, LTR_ERR_UNSUPPORTED, "target map has %lld < k = %d points (the reference divides a partial sum by k / crashes on an empty tree)", (long long)tp->n, k);
+    if (tp->n < 1) return fail(ctx, LTR_ERR_UNSUPPORTED, "empty target map (PCL's nearestKSearch asserts on an empty tree)");
+    const bool small = tp->n < k;   // fewer than k target points: all of them are returned and the sum is still divided by k (Session.cpp:592-594)
     const DevScanSet scans = *sp;
     const DevPoses poses = *pp;
     const DevCloud target = *tp;
@@ -239,11 +265,13 @@ int ltr_knn_diff(ltr_ctx* ctx, ltr_scanset scans_h, ltr_poses poses_h, int32_t p
     uint8_t* label = nullptr;
     float *gx = nullptr, *gy = nullptr, *gz = nullptr;
     if (n > 0) {
-        LTR_TRY(build_grid(ctx, target, k, thr, &gb));
+        PtrView small_view{nullptr, nullptr, nullptr, nullptr, 0};
+        if (small) small_view = view(target);
+        else LTR_TRY(build_grid(ctx, target, k, thr, &gb));
         LTR_TRY(dev_alloc(ctx, &p, (size_t)n * (3 * sizeof(float) + 1) + 64));
         gx = (float*)p; gy = gx + n; gz = gy + n; label = (uint8_t*)(gz + n);
         knn_scan_label_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(view(scans.pts), scans.d_off, scans.K, poses.d, pose_offset, ctx->d_ext,
-            ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, gb.g, gb.cell_start, gb.sorted, k, thr, label, gx, gy, gz);
+            ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, gb.g, gb.cell_start, gb.sorted, k, thr, label, gx, gy, gz, small_view);
         LTR_LAUNCH_CHECK(ctx);
         g_grid.release();
         // re-localise in place (every point; partitioning afterwards keeps the arithmetic identical to the reference,
@@ -252,11 +280,13 @@ int ltr_knn_diff(ltr_ctx* ctx, ltr_scanset scans_h, ltr_poses poses_h, int32_t p
         DevCloud tmp = scans.pts;  // reuse layout: write relocalised xyz into a scratch cloud with the same stride
         ltr_cloud scratch;
         LTR_TRY(cloud_new(ctx, n, &scratch));
+        struct CloudGuard { ltr_ctx* c; ltr_cloud h; bool armed; ~CloudGuard() { if (armed) ltr_cloud_free(c, h); } } g_scratch{ctx, scratch, true};   // error paths below
         DevCloud sc = ctx->clouds[scratch];
         knn_relocalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(gx, gy, gz, n, scans.d_off, scans.K, poses.d, pose_offset, ctx->d_ext,
             ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, sc.x(), sc.y(), sc.z());
         LTR_LAUNCH_CHECK(ctx);
         LTR_CUDA(ctx, cudaMemcpyAsync(sc.i(), tmp.i(), (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        g_scratch.armed = false;
         DevScanSet view_set = scans;
         view_set.pts = sc;
         const int rc = split_scanset_by_flag(ctx, view_set, label, out_coexist, out_diff);
@@ -278,18 +308,21 @@ int ltr_knn_split_cloud(ltr_ctx* ctx, ltr_cloud query_h, ltr_cloud target_h, int
     LTR_TRY(cloud_get(ctx, target_h, &tp));
     if (k < 1 || k > kMaxK) return fail(ctx, LTR_ERR_UNSUPPORTED, "k = %d outside [1, %d]", k, kMaxK);
     if (!(thr > 0.0f)) return fail(ctx, LTR_ERR_INVALID, "threshold must be positive");
-    if (tp->n < k) return fail(ctx, LTR_ERR_UNSUPPORTED, "target has %lld < k = %d points", (long long)tp->n, k);
+    if (tp->n < 1) return fail(ctx, LTR_ERR_UNSUPPORTED, "empty target (PCL's nearestKSearch asserts on an empty tree)");
+    const bool small = tp->n < k;
     const DevCloud q = *qp, target = *tp;
     LTR_TRY(cloud_new(ctx, q.n, out_near));
     LTR_TRY(cloud_new(ctx, q.n, out_far));
     if (q.n == 0) return LTR_OK;
     GridBuf gb;
     ScratchGuard g_grid(ctx, &gb.block);
-    LTR_TRY(build_grid(ctx, target, k, thr, &gb));
+    PtrView small_view{nullptr, nullptr, nullptr, nullptr, 0};
+    if (small) small_view = view(target);
+    else LTR_TRY(build_grid(ctx, target, k, thr, &gb));
     void* p = nullptr;
     ScratchGuard g_p(ctx, &p);
     LTR_TRY(dev_alloc(ctx, &p, (size_t)q.n));
-    knn_cloud_label_kernel<<<(unsigned)((q.n + 127) / 128), 128, 0, ctx->stream>>>(view(q), gb.g, gb.cell_start, gb.sorted, k, thr, (uint8_t*)p);
+    knn_cloud_label_kernel<<<(unsigned)((q.n + 127) / 128), 128, 0, ctx->stream>>>(view(q), gb.g, gb.cell_start, gb.sorted, k, thr, (uint8_t*)p, small_view);
     LTR_LAUNCH_CHECK(ctx);
     g_grid.release();
     DevCloud o0 = ctx->clouds[*out_near], o1 = ctx->clouds[*out_far];

@@ -204,6 +204,14 @@ static void make_kf_fast(const double* inv_pose /*12*/, const double* b2l /*16*/
     const double a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[6], g = M[8], h = M[9], i = M[10];
     const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
     bool ok = std::isfinite(det) && std::fabs(det) > 1e-6 && std::fabs(det) < 1e6;
+    // The error budget of the fast path (project_fast.cuh) and the bounding-sphere / cone bound of the tile culling (project_cull.cuh)
+    // assume a RIGID transform: rows of unit length, mutually orthogonal.  A scaled or sheared inverse pose / extrinsic keeps the
+    // reference arithmetic only (ok = 0 -> every pair of this keyframe takes the exact path).
+    for (int r1 = 0; r1 < 3 && ok; ++r1)
+        for (int r2 = r1; r2 < 3; ++r2) {
+            const double dot = M[r1 * 4 + 0] * M[r2 * 4 + 0] + M[r1 * 4 + 1] * M[r2 * 4 + 1] + M[r1 * 4 + 2] * M[r2 * 4 + 2];
+            if (!(std::fabs(dot - (r1 == r2 ? 1.0 : 0.0)) < 1e-5)) ok = false;
+        }
     double inv[9] = {(e * i - f * h), (c * h - b * i), (b * f - c * e), (f * g - d * i), (a * i - c * g), (c * d - a * f), (d * h - e * g), (b * g - a * h), (a * e - b * d)};
     double cc[3] = {0, 0, 0};
     if (ok) for (int r = 0; r < 3; ++r) cc[r] = -(inv[r * 3 + 0] * M[3] + inv[r * 3 + 1] * M[7] + inv[r * 3 + 2] * M[11]) / det;
@@ -290,6 +298,7 @@ void ltr_destroy(ltr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->trace) ltr_trace_dump(ctx, 1);
+    for (size_t i = 0; i < ctx->nccl.size(); ++i) if (ctx->nccl[i].used) ltr_nccl_destroy(ctx, (int32_t)i);
     for (auto& c : ctx->clouds) if (c.used) cloud_release(ctx, &c);
     for (auto& s : ctx->scansets) if (s.used) { cloud_release(ctx, &s.pts); dev_free(ctx, s.d_off); }
     for (auto& p : ctx->poses) if (p.used) { dev_free(ctx, p.d); dev_free(ctx, p.d_fast); }
@@ -310,12 +319,14 @@ void ltr_destroy(ltr_ctx* ctx) {
 const char* ltr_last_error(const ltr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 int ltr_synchronize(ltr_ctx* ctx) {
+    ApiTrace tr__(ctx, "ltr_synchronize");
     if (!ctx) return LTR_ERR_INVALID;
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return LTR_OK;
 }
 
 int64_t ltr_kernel_launches(const ltr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* ltr_stream_handle(ltr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int64_t ltr_voxel_shortcuts(const ltr_ctx* ctx) { return ctx ? ctx->vox_shortcuts : 0; }
 int ltr_memory_stats(const ltr_ctx* ctx, int64_t* stats3) {
     if (!ctx || !stats3) return LTR_ERR_INVALID;
@@ -330,6 +341,7 @@ int ltr_cloud_upload(ltr_ctx* ctx, const float* xyzi, int64_t n, ltr_cloud* out)
     return upload_points(ctx, xyzi, ctx->clouds[*out]);
 }
 int ltr_cloud_alloc(ltr_ctx* ctx, int64_t n, ltr_cloud* out) {
+    ApiTrace tr__(ctx, "ltr_cloud_alloc");
     if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
     return cloud_new(ctx, n, out);
 }
@@ -405,6 +417,7 @@ int ltr_scanset_info(ltr_ctx* ctx, ltr_scanset s, int32_t* K, int64_t* total) {
     return LTR_OK;
 }
 int ltr_scanset_download(ltr_ctx* ctx, ltr_scanset s, float* xyzi, int64_t capacity, int64_t* offsets) {
+    ApiTrace tr__(ctx, "ltr_scanset_download");
     DevScanSet* ss;
     LTR_TRY(scanset_get(ctx, s, &ss));
     if (offsets) std::memcpy(offsets, ss->h_off.data(), (size_t)(ss->K + 1) * sizeof(int64_t));
@@ -481,6 +494,7 @@ int ltr_poses_upload(ltr_ctx* ctx, const double* poses, const double* inv_poses,
     return LTR_OK;
 }
 int ltr_poses_free(ltr_ctx* ctx, ltr_poses h) {
+    ApiTrace tr__(ctx, "ltr_poses_free");
     DevPoses* p;
     LTR_TRY(poses_get(ctx, h, &p));
     dev_free(ctx, p->d);
@@ -519,11 +533,13 @@ int ltr_trace_dump(ltr_ctx* ctx, int reset) {
 }
 
 int ltr_timer_start(ltr_ctx* ctx) {
+    ApiTrace tr__(ctx, "ltr_timer_start");
     if (!ctx) return LTR_ERR_INVALID;
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev_timer0, ctx->stream));
     return LTR_OK;
 }
 int ltr_timer_stop(ltr_ctx* ctx, double* ms) {
+    ApiTrace tr__(ctx, "ltr_timer_stop");
     if (!ctx || !ms) return LTR_ERR_INVALID;
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev_timer1, ctx->stream));
     LTR_CUDA(ctx, cudaEventSynchronize(ctx->ev_timer1));
@@ -534,6 +550,7 @@ int ltr_timer_stop(ltr_ctx* ctx, double* ms) {
 }
 
 int ltr_last_pass_stats(ltr_ctx* ctx, double* s) {
+    ApiTrace tr__(ctx, "ltr_last_pass_stats");
     if (!ctx || !s) return LTR_ERR_INVALID;
     if (ctx->stats_counters_pending) {
         unsigned long long c[4] = {0, 0, 0, 0};

@@ -42,6 +42,15 @@ struct DevPoses {
 
 struct PtrView { const float *x, *y, *z, *i; int64_t n; };
 
+// one NCCL communicator of a context (nccl_comm.cu)
+struct NcclComm {
+    void* comm = nullptr;       // ncclComm_t
+    int rank = 0, world = 1;
+    bool used = false;
+    int64_t* h_cnt = nullptr;   // pinned scratch for size exchanges
+    int64_t* d_cnt = nullptr;   // device scratch for size exchanges
+};
+
 }  // namespace ltr
 
 struct ltr_ctx {
@@ -54,6 +63,7 @@ struct ltr_ctx {
     std::vector<ltr::DevCloud> clouds;
     std::vector<ltr::DevScanSet> scansets;
     std::vector<ltr::DevPoses> poses;
+    std::vector<ltr::NcclComm> nccl;           // communicators created by ltr_nccl_init / ltr_nccl_split
     int64_t launches = 0;
     int64_t vox_shortcuts = 0;   // voxelisations answered by the already-one-point-per-voxel shortcut (util.cu)
     bool ext_identity = true;     // base2lidar/lidar2base exactly identity -> second transform step is exact and skipped
@@ -102,12 +112,24 @@ int fail(ltr_ctx* ctx, int code, const char* fmt, ...);
                                                    cudaGetErrorString(e__), __FILE__, __LINE__);      \
     } while (0)
 
-// per-entry-point host timing (only when LTR_TRACE=1; adds two stream synchronisations per call)
+// Entry-point guard: makes the context's GPU the calling thread's current device for the duration of the call (the caller may have
+// switched devices -- torch.cuda.set_device, a second context on another GPU -- and cudaMalloc / kernel launches follow the CURRENT
+// device) and restores the previous one afterwards; with LTR_TRACE=1 it also times the call on the host between two stream
+// synchronisations.
 struct ApiTrace {
-    ltr_ctx* c; const char* name; double t0;
+    ltr_ctx* c; const char* name; double t0; int prev_dev = -1;
     static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-    ApiTrace(ltr_ctx* ctx, const char* n) : c(ctx), name(n), t0(0) { if (c && c->trace) { cudaStreamSynchronize(c->stream); t0 = now(); } }
-    ~ApiTrace() { if (c && c->trace) { cudaStreamSynchronize(c->stream); auto& a = c->trace_acc[name]; a.first += now() - t0; a.second += 1; } }
+    ApiTrace(ltr_ctx* ctx, const char* n) : c(ctx), name(n), t0(0) {
+        if (!c) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != c->device) { prev_dev = cur; cudaSetDevice(c->device); }
+        if (c->trace) { cudaStreamSynchronize(c->stream); t0 = now(); }
+    }
+    ~ApiTrace() {
+        if (!c) return;
+        if (c->trace) { cudaStreamSynchronize(c->stream); auto& a = c->trace_acc[name]; a.first += now() - t0; a.second += 1; }
+        if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    }
 };
 
 // allocation helpers (stream-ordered)

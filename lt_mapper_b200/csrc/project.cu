@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) scan_rimg_kernel(PtrView scans, const int
 // angle polynomials are approximate; the column / row are accepted when every value within the margins (the ones validated for the map
 // projection, which additionally cover a transform error that does not exist here) rounds to the same pixel, otherwise -- pixel
 // boundary, point on the z axis -- the reference arithmetic decides.  The range written is always the exact one.
+template <bool kElDirect>
 __global__ void __launch_bounds__(256) scan_rimg_fast_kernel(PtrView scans, const int64_t* __restrict__ off, int kf0, int nb, ImgShape g, FastCfg fc,
                                                              uint32_t* __restrict__ rimg) {
     const int64_t begin = off[kf0], end = off[kf0 + nb];
@@ -60,10 +61,10 @@ __global__ void __launch_bounds__(256) scan_rimg_fast_kernel(PtrView scans, cons
     if (i >= end) return;
     const int k = find_kf_rel(off + kf0, nb, i);
     const float x = scans.x[i], y = scans.y[i], z = scans.z[i];
-    const FastProj f = fast_sph(x, y, z);
+    const FastProj f = fast_sph<kElDirect>(x, y, z);
     int r, c;
     const bool okc = certain_round(__fmaf_rn(f.az, fc.col_scale, fc.col_off), __fmaf_rn(fc.m_col_b, f.rho_inv_r, fc.m_col_a), g.cols - 1, &c);
-    const bool okr = certain_round(__fmaf_rn(-f.el, fc.row_scale, fc.row_off), fc.m_row, g.rows - 1, &r);
+    const bool okr = certain_round(__fmaf_rn(f.el, fc.neg_row_scale, fc.row_off), fc.m_row, g.rows - 1, &r);
     float range;
     if (okc & okr) {
         range = __fsqrt_rn(fa(fa(fm(x, x), fm(y, y)), fm(z, z)));   // cart2sph's r (utility.cpp:48)
@@ -73,6 +74,15 @@ __global__ void __launch_bounds__(256) scan_rimg_fast_kernel(PtrView scans, cons
         range = s.r;
     }
     atomicMin(&rimg[(size_t)k * g.rows * g.cols + (size_t)r * g.cols + c], __float_as_uint(range));
+}
+
+// test image of the scan-minus-map fast path (project_fast.cuh): the scan image with "no return" pixels set to -inf, which makes
+// "scan - range > thres" false for every range -- valid when no map point can be ~10000 m away (empty_scan_shortcut_ok)
+__global__ void __launch_bounds__(256) scan_test_image_kernel(const uint32_t* __restrict__ rimg, uint32_t* __restrict__ test_img, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = rimg[i];
+        test_img[i] = (b == kNoPointBits) ? 0xff800000u : b;
+    }
 }
 
 // Exact projection of every map point into every keyframe of the batch.
@@ -255,15 +265,16 @@ static int empty_scan_shortcut_ok(ltr_ctx* ctx, const DevCloud& map, const DevPo
     return LTR_OK;
 }
 
+template <bool kElDirect>
 __global__ void debug_fast_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ kf, const double* __restrict__ pose,
                                   const double* __restrict__ ext, int ext_identity, int order, ImgShape g, FastCfg fc,
                                   float* __restrict__ out /* n x 8: vcol_f vrow_f r_f rho_inv_r | vcol_e vrow_e r_e unused */) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
-    const FastProj f = fast_project(kf, x, y, z);
+    const FastProj f = fast_project<kElDirect>(kf, x, y, z);
     out[8 * i + 0] = __fmaf_rn(f.az, fc.col_scale, fc.col_off);
-    out[8 * i + 1] = __fmaf_rn(-f.el, fc.row_scale, fc.row_off);
+    out[8 * i + 1] = __fmaf_rn(f.el, fc.neg_row_scale, fc.row_off);
     out[8 * i + 2] = f.r;
     out[8 * i + 3] = f.rho_inv_r;
     float lx, ly, lz;
@@ -277,14 +288,51 @@ __global__ void debug_fast_kernel(const float* __restrict__ xyz, int64_t n, cons
     out[8 * i + 7] = 0.0f;
 }
 
+// Exhaustive check of the two arctangent polynomials of the fast path: every float a with bits in [0, last_bits] (i.e. all of [0, 1]
+// or [0, 0.5]) is evaluated and compared with atan((double)a); the maximum absolute error is kept (positive doubles order like their bits).
+__global__ void __launch_bounds__(256) atan_sweep_kernel(int which, uint32_t last_bits, unsigned long long* __restrict__ max_err_bits, uint32_t* __restrict__ arg_bits) {
+    double worst = 0.0;
+    uint32_t worst_arg = 0;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= last_bits; b += (uint64_t)gridDim.x * blockDim.x) {
+        const float a = __uint_as_float((uint32_t)b);
+        const float v = which == 0 ? fast_atan01(a) : fast_atan_half(a);
+        const double e = fabs((double)v - atan((double)a));
+        if (e > worst) { worst = e; worst_arg = (uint32_t)b; }
+    }
+    const unsigned long long wb = (unsigned long long)__double_as_longlong(worst);
+    const unsigned long long old = atomicMax(max_err_bits, wb);
+    if (wb > old) *arg_bits = worst_arg;   // racy between equal-ish maxima; the argument is informational only
+}
+
 // persistent grid: 4 resident CTAs per SM (64 registers, ~22 KB shared memory each), never more CTAs than tiles need
 static inline unsigned fast_grid(const ltr_ctx* ctx, int64_t n) {
     const int64_t tiles = (n + 32 * kFastPts - 1) / (32 * kFastPts);
     const int64_t ctas = (tiles + kFastThreads / 32 - 1) / (kFastThreads / 32);
-    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)ctx->sm_count * 4));
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)ctx->sm_count * kFastCtasPerSm));
 }
 
-static inline size_t fast_smem_bytes(int nb) { return (size_t)((nb * 16 + 3) & ~3) * sizeof(float) + (size_t)(kFastThreads / 32) * 2 * kQueueCap * sizeof(uint64_t); }
+static inline size_t fast_smem_bytes() { return (size_t)(kFastThreads / 32) * 2 * kQueueCap * sizeof(uint64_t); }
+
+static inline KfBatch make_kf_batch(const DevPoses& poses, int k0, int nb) {
+    KfBatch kb;
+    std::memset(&kb, 0, sizeof(kb));
+    std::memcpy(kb.kf, &poses.h_fast[(size_t)k0 * 16], (size_t)nb * 16 * sizeof(float));
+    return kb;
+}
+
+// one launch of the fast projection over the keyframes [k0, k0 + nb) of `poses`
+template <bool kCand>
+static void launch_fast(ltr_ctx* ctx, const DevCloud& map, const DevPoses& poses, int k0, int nb, const ImgShape& g, const FastCfg& fc,
+                        const uint32_t* rimg, const uint32_t* test_img, float thres, uint64_t* win, uint32_t* amin, const CullArgs& ca) {
+    const unsigned fb = fast_grid(ctx, map.n);
+    unsigned int* work = (unsigned int*)(ctx->d_counters + 4);
+    cudaMemsetAsync(work, 0, sizeof(unsigned int), ctx->stream);
+    const KfBatch kb = make_kf_batch(poses, k0, nb);
+    if (fc.el_direct) map_project_fast_kernel<kCand, true><<<fb, kFastThreads, fast_smem_bytes(), ctx->stream>>>(view(map), kb, poses.d, k0, nb, ctx->d_ext,
+        ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, test_img, thres, win, amin, ca, ctx->d_counters, work);
+    else map_project_fast_kernel<kCand, false><<<fb, kFastThreads, fast_smem_bytes(), ctx->stream>>>(view(map), kb, poses.d, k0, nb, ctx->d_ext,
+        ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, test_img, thres, win, amin, ca, ctx->d_counters, work);
+}
 
 static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, max_blocks));
@@ -317,9 +365,10 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     if (!accumulate && map->n > 0) LTR_CUDA(ctx, cudaMemsetAsync(map->flags, 0, (size_t)map->n, ctx->stream));
     const ImgShape g{rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg};
     const int64_t npx = (int64_t)rows * cols;
-    const int B = std::max(1, std::min(ctx->cfg.keyframe_batch, kf_end - kf_begin));
     const bool cand = (mode != LTR_MODE_ND);
-    const bool use_fast = ctx->cfg.fast_path && npx <= (1 << 18) && B <= (1 << 12);   // queue-entry field widths, 32-bit pixel offsets (project_fast.cuh)
+    const bool use_fast = ctx->cfg.fast_path && npx <= (1 << 18);   // queue-entry field widths, 32-bit pixel offsets (project_fast.cuh)
+    // fast path: at most kFastMaxBatch keyframes per launch (their constants travel as a kernel parameter); exact path: 12 doubles of shared memory per keyframe
+    const int B = std::max(1, std::min(std::min(ctx->cfg.keyframe_batch, use_fast ? kFastMaxBatch : 400), kf_end - kf_begin));
     int shortcut = 0;
     if (use_fast && cand && map->n > 0 && kf_end > kf_begin) LTR_TRY(empty_scan_shortcut_ok(ctx, *map, *poses, kf_begin, kf_end, &shortcut));
     const FastCfg fc = make_fast_cfg(rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, shortcut);
@@ -352,10 +401,11 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     if (map->n > 0 && kf_end > kf_begin) {
         void *p_rimg = nullptr, *p_win = nullptr;
         ScratchGuard g_rimg(ctx, &p_rimg), g_win(ctx, &p_win);
-        LTR_TRY(dev_alloc(ctx, &p_rimg, (size_t)B * npx * sizeof(uint32_t) * (use_fast ? 2 : 1)));
+        LTR_TRY(dev_alloc(ctx, &p_rimg, (size_t)B * npx * sizeof(uint32_t) * (use_fast ? 3 : 1)));
         LTR_TRY(dev_alloc(ctx, &p_win, (size_t)B * npx * sizeof(uint64_t)));
         uint32_t* rimg = (uint32_t*)p_rimg;
         uint32_t* amin = rimg + (size_t)B * npx;   // approximate running minimum (fast path only)
+        uint32_t* timg = amin + (size_t)B * npx;   // test image of the scan-minus-map variants when pixels without a return can never flag
         uint64_t* win = (uint64_t*)p_win;
         const int fill_blocks = ctx->sm_count * 8;
         fill_u64_kernel<<<grid_for(B * npx, 256, fill_blocks), 256, 0, ctx->stream>>>(win, cand ? kWinNone : kWinEmpty, B * npx);
@@ -371,7 +421,8 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
 
             const int64_t npts = scans->h_off[k0 + nb] - scans->h_off[k0];
             if (npts > 0) {
-                if (use_fast) scan_rimg_fast_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, k0, nb, g, fc, rimg);
+                if (use_fast && fc.el_direct) scan_rimg_fast_kernel<true><<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, k0, nb, g, fc, rimg);
+                else if (use_fast) scan_rimg_fast_kernel<false><<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, k0, nb, g, fc, rimg);
                 else scan_rimg_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, k0, nb, g, rimg);
                 LTR_LAUNCH_CHECK(ctx);
             }
@@ -380,17 +431,17 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
                 scan_pyramid_kernel<<<(unsigned)nb, 1024, 0, ctx->stream>>>(rimg, nb, rows, cols, empty_value, ca, (float*)p_pyr);
                 LTR_LAUNCH_CHECK(ctx);
             }
+            const uint32_t* test_img = rimg;
+            if (use_fast && cand && shortcut) {
+                scan_test_image_kernel<<<grid_for(nb * npx, 256, fill_blocks), 256, 0, ctx->stream>>>(rimg, timg, nb * npx);
+                LTR_LAUNCH_CHECK(ctx);
+                test_img = timg;
+            }
             prof_begin(ctx);
             launch_units.push_back(nb);
             if (use_fast) {
-                const unsigned fb = fast_grid(ctx, map->n);
-                const size_t fsmem = fast_smem_bytes(nb);
-                unsigned int* work = (unsigned int*)(ctx->d_counters + 4);
-                LTR_CUDA(ctx, cudaMemsetAsync(work, 0, sizeof(unsigned int), ctx->stream));
-                if (cand) map_project_fast_kernel<true><<<fb, kFastThreads, fsmem, ctx->stream>>>(view(*map), poses->d_fast, poses->d, k0, nb, ctx->d_ext,
-                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, diff_thres, win, amin, ca, ctx->d_counters, work);
-                else map_project_fast_kernel<false><<<fb, kFastThreads, fsmem, ctx->stream>>>(view(*map), poses->d_fast, poses->d, k0, nb, ctx->d_ext,
-                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, diff_thres, win, amin, ca, ctx->d_counters, work);
+                if (cand) launch_fast<true>(ctx, *map, *poses, k0, nb, g, fc, rimg, test_img, diff_thres, win, amin, ca);
+                else launch_fast<false>(ctx, *map, *poses, k0, nb, g, fc, rimg, amin, diff_thres, win, amin, ca);
             } else {
                 const unsigned mb = (unsigned)((map->n + 255) / 256);
                 const size_t smem = (size_t)nb * 12 * sizeof(double);
@@ -441,7 +492,7 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
     const DevPoses posc = *poses;
     std::vector<int64_t> off((size_t)K + 1, 0);
     const FastCfg fc = make_fast_cfg(rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, 0);
-    const bool use_fast = ctx->cfg.fast_path && npx <= (1 << 18) && ctx->cfg.keyframe_batch <= (1 << 12);
+    const bool use_fast = ctx->cfg.fast_path && npx <= (1 << 18);
     if (use_fast) LTR_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     void *p_list = nullptr, *p_cnt = nullptr;
@@ -449,7 +500,7 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
     std::vector<int> launch_units;
     ctx->ev_used = 0;
     if (K > 0 && mapc.n > 0) {
-        const int B = std::max(1, std::min(ctx->cfg.keyframe_batch, K));
+        const int B = std::max(1, std::min(std::min(ctx->cfg.keyframe_batch, use_fast ? kFastMaxBatch : 400), K));
         void *p_win = nullptr, *p_amin = nullptr;
         ScratchGuard g_win(ctx, &p_win), g_amin(ctx, &p_amin);
         LTR_TRY(dev_alloc(ctx, &p_win, (size_t)B * npx * sizeof(uint64_t)));
@@ -469,13 +520,9 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
             if (use_fast) {
                 fill_u32_kernel<<<grid_for(nb * npx, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(amin, 0x7f800000u, nb * npx);
                 LTR_LAUNCH_CHECK(ctx);
-                const unsigned fb = fast_grid(ctx, mapc.n);
                 CullArgs no_cull;
                 std::memset(&no_cull, 0, sizeof(no_cull));
-                unsigned int* work = (unsigned int*)(ctx->d_counters + 4);
-                LTR_CUDA(ctx, cudaMemsetAsync(work, 0, sizeof(unsigned int), ctx->stream));
-                map_project_fast_kernel<false><<<fb, kFastThreads, fast_smem_bytes(nb), ctx->stream>>>(view(mapc), posc.d_fast, posc.d, kf_begin + k0, nb, ctx->d_ext,
-                    ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, nullptr, 0.0f, win, amin, no_cull, ctx->d_counters, work);
+                launch_fast<false>(ctx, mapc, posc, kf_begin + k0, nb, g, fc, nullptr, amin, 0.0f, win, amin, no_cull);
             } else {
                 const unsigned mb = (unsigned)((mapc.n + 255) / 256);
                 map_project_kernel<false><<<mb, 256, (size_t)nb * 12 * sizeof(double), ctx->stream>>>(view(mapc), posc.d, kf_begin + k0, nb, ctx->d_ext,
@@ -519,6 +566,7 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
 
 int ltr_debug_pixel_index(ltr_ctx* ctx, const float* xyz, int64_t n, int32_t rows, int32_t cols, int32_t* row, int32_t* col, float* range,
                           float* az, float* el) {
+    ApiTrace tr__(ctx, "ltr_debug_pixel_index");
     if (!ctx || !xyz || n < 0) return fail(ctx, LTR_ERR_INVALID, "bad argument");
     if (n == 0) return LTR_OK;
     void* p = nullptr;
@@ -544,7 +592,36 @@ int ltr_debug_pixel_index(ltr_ctx* ctx, const float* xyz, int64_t n, int32_t row
     return LTR_OK;
 }
 
+int ltr_debug_margins(ltr_ctx* ctx, float res_alpha, float* m) {
+    if (!ctx || !m) return fail(ctx, LTR_ERR_INVALID, "bad argument");
+    int32_t rows, cols;
+    ltr_reset_rimg_size(ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, res_alpha, &rows, &cols);
+    const FastCfg fc = make_fast_cfg(rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, 0);
+    m[0] = fc.m_col_a; m[1] = fc.m_col_b; m[2] = fc.m_row; m[3] = fc.m_r_rel; m[4] = fc.m_r_abs; m[5] = (float)fc.el_direct;
+    m[6] = (float)((fc.m_col_a + fc.m_col_b) / kMarginSafety); m[7] = (float)(fc.m_row / kMarginSafety);
+    return LTR_OK;
+}
+
+int ltr_debug_atan_sweep(ltr_ctx* ctx, int32_t which, double* max_abs_err, float* arg_at_max) {
+    ApiTrace tr__(ctx, "ltr_debug_atan_sweep");
+    if (!ctx || !max_abs_err || (which != 0 && which != 1)) return fail(ctx, LTR_ERR_INVALID, "bad argument");
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
+    LTR_TRY(dev_alloc(ctx, &p, 16));
+    LTR_CUDA(ctx, cudaMemsetAsync(p, 0, 16, ctx->stream));
+    const uint32_t last = which == 0 ? 0x3F800000u : 0x3F000000u;   // 1.0f / 0.5f
+    atan_sweep_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(which, last, (unsigned long long*)p, (uint32_t*)((char*)p + 8));
+    LTR_LAUNCH_CHECK(ctx);
+    unsigned long long h[2] = {0, 0};
+    LTR_CUDA(ctx, cudaMemcpyAsync(h, p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(max_abs_err, &h[0], 8);
+    if (arg_at_max) { const uint32_t b = (uint32_t)h[1]; std::memcpy(arg_at_max, &b, 4); }
+    return LTR_OK;
+}
+
 int ltr_debug_scan_rimg(ltr_ctx* ctx, ltr_scanset scans_h, int32_t kf, float res_alpha, float* out) {
+    ApiTrace tr__(ctx, "ltr_debug_scan_rimg");
     if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
     DevScanSet* scans;
     LTR_TRY(scanset_get(ctx, scans_h, &scans));
@@ -561,9 +638,11 @@ int ltr_debug_scan_rimg(ltr_ctx* ctx, ltr_scanset scans_h, int32_t kf, float res
     LTR_LAUNCH_CHECK(ctx);
     const int64_t npts = scans->h_off[kf + 1] - scans->h_off[kf];
     if (npts > 0) {
-        if (ctx->cfg.fast_path && npx <= (1 << 18))
-            scan_rimg_fast_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, kf, 1, g,
-                make_fast_cfg(rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, 0), (uint32_t*)p);
+        const FastCfg fcd = make_fast_cfg(rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, 0);
+        if (ctx->cfg.fast_path && npx <= (1 << 18) && fcd.el_direct)
+            scan_rimg_fast_kernel<true><<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, kf, 1, g, fcd, (uint32_t*)p);
+        else if (ctx->cfg.fast_path && npx <= (1 << 18))
+            scan_rimg_fast_kernel<false><<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, kf, 1, g, fcd, (uint32_t*)p);
         else scan_rimg_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(view(scans->pts), scans->d_off, kf, 1, g, (uint32_t*)p);
         LTR_LAUNCH_CHECK(ctx);
     }
@@ -573,6 +652,7 @@ int ltr_debug_scan_rimg(ltr_ctx* ctx, ltr_scanset scans_h, int32_t kf, float res
 }
 
 int ltr_debug_fast_project(ltr_ctx* ctx, const float* xyz, int64_t n, const double* inv_pose16, float res_alpha, float* out8, float* margins4) {
+    ApiTrace tr__(ctx, "ltr_debug_fast_project");
     if (!ctx || !xyz || !inv_pose16 || !out8 || n < 0) return fail(ctx, LTR_ERR_INVALID, "bad argument");
     int32_t rows, cols;
     ltr_reset_rimg_size(ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, res_alpha, &rows, &cols);
@@ -591,7 +671,9 @@ int ltr_debug_fast_project(ltr_ctx* ctx, const float* xyz, int64_t n, const doub
     float* d_xyz = (float*)p;
     float* d_out = d_xyz + 3 * n;
     LTR_CUDA(ctx, cudaMemcpyAsync(d_xyz, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
-    debug_fast_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, pp.d_fast, pp.d, ctx->d_ext, ctx->ext_identity ? 1 : 0,
+    if (fc.el_direct) debug_fast_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, pp.d_fast, pp.d, ctx->d_ext, ctx->ext_identity ? 1 : 0,
+                                                                        ctx->cfg.transform_order, g, fc, d_out);
+    else debug_fast_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, pp.d_fast, pp.d, ctx->d_ext, ctx->ext_identity ? 1 : 0,
                                                                         ctx->cfg.transform_order, g, fc, d_out);
     LTR_LAUNCH_CHECK(ctx);
     LTR_CUDA(ctx, cudaMemcpyAsync(out8, d_out, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));

@@ -28,14 +28,47 @@ struct FastCfg {
     float m_row;                // row margin [px]
     float m_r_rel, m_r_abs;     // range margin [m] = m_r_abs + m_r_rel * r
     int empty_scan_shortcut;    // 1: no map point can be >= 9000 m from a keyframe -> pixels without a scan return never flag
+    // folded forms of the above, so that the hot loop takes them straight from the constant bank
+    float lim_c, lim_r;         // 0.5 - m_col_a, 0.5 - m_row
+    float rel_m1;               // m_r_rel - 1
+    float mr2_rel, mr2_abs;     // 2 * m_r_rel, 2 * m_r_abs
+    float neg_row_scale;
+    int el_direct;              // 1: |elevation| beyond atan(0.5) clamps to the first / last row with room to spare -> short elevation path
 };
 
-// Deviation budget (validated by ltr_debug_fast_project over >1e8 samples, see test): the fast pre-round pixel
-// coordinate differs from the reference's own pre-round float by
-//   transform: |dq| <= ~6e-7 * r per component  -> azimuth 6e-7 * r/rho rad, elevation ~1e-6 rad
-//   atan (degree-8 minimax in a^2, approximate reciprocal): <= 3e-7 rad;  quadrant fix-ups <= 3e-7 rad
-//   reference's own float chain (rad2deg rounding, (x + H/2)/H, scaling): <= 4e-7 * C px
-// Margins are set >= 3x the measured maxima (measured: deviation / margin <= 0.26 / 0.23 / 0.21 for column / row / range).
+// ---------------------------------------------------------------------------------------------------------------------------
+// Error budget of the fast evaluation against the REFERENCE's own pre-round pixel coordinates and range (DESIGN.md section 4.1
+// derives each line; u = 2^-24 is the unit roundoff of a correctly rounded f32 operation, MUFU.RCP is within 2^-23 and MUFU.RSQ
+// within 2^-22.4 relative (PTX ISA, rcp/rsqrt.approx.ftz.f32); tests/test_gpu_fastpath.py sweeps EVERY float of [0, 1] through both
+// polynomials and asserts the two constants marked (*), and checks measured deviations of whole projections against the margins).
+//   q_fast:  dx = fl(p - c_hi) (u |d|), three chained FMAs with f32-rounded matrix entries  ->  |dq_i| <= 5 u r per component
+//   q_ref :  double transform rounded once to f32                                               ->  |dq_i| <= u |q_i|
+// Azimuth [rad]                                            fast                                  reference chain (utility.cpp:46, 53-56, 123)
+//   from dq                                                5 sqrt(2) u r / rho = 4.3e-7 r/rho    u                      = 0.6e-7
+//   a = min * rcp(max): (2^-23 + u) * a / (1 + a^2)        0.9e-7                                atan2f (fdlibm, < 1 ulp of pi) 2.4e-7
+//   7-coefficient polynomial incl. its f32 evaluation (*)  6.8e-7                                rad2deg: f64, rounded to f32   1.9e-7
+//   quadrant fix-ups (f32 constants and subtractions)      3.2e-7                                deg + H/2 (0.5 ulp of 360)     2.7e-7
+//   sum                                                    1.09e-6 + 4.3e-7 r/rho                7.6e-7
+//   pixel-space roundings (fma / divide / scale)           1.5 u C                               2 u C
+// Elevation [rad], short path |qz / rho| <= 0.5
+//   from dq                                                5.2e-7                                u                      = 0.6e-7
+//   t = qz * rsq(rho^2): (2^-22.4 + u) * t / (1 + t^2)     1.0e-7                                atan2f (< 1 ulp of pi/2)       1.2e-7
+//   5-coefficient polynomial incl. its f32 evaluation (*)  0.9e-7                                rad2deg + (deg + V/2)          1.6e-7
+//   sum                                                    7.1e-7                                3.4e-7
+//   pixel-space roundings                                  1.5 u R                               3 u R
+// Range (relative): MUFU.RSQ 1.8e-7 + r^2 accumulation 3 u + dq 5 sqrt(3) u = 9.4e-7 (fast) + 2.5 u (reference) = 1.1e-6
+// The margins below are these sums times kMarginSafety.  NaN or infinity anywhere fails every comparison -> exact path.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr double kMarginSafety = 1.5;
+constexpr double kU = 5.9604644775390625e-08;
+constexpr double kAzPolyErr = 6.8e-7;    // (*) max |fast_atan01(a) - atan(a)| over all floats a in [0, 1]
+constexpr double kElPolyErr = 0.9e-7;    // (*) max |fast_atan_half(t) - atan(t)| over all floats |t| <= 0.5
+constexpr double kAzFixed = (kU + 2.4e-7 + 1.9e-7 + 2.7e-7) + (0.9e-7 + kAzPolyErr + 3.2e-7);   // rad, independent of r/rho
+constexpr double kAzPerRhoInvR = 4.3e-7;                                                        // rad per unit of r/rho
+constexpr double kElFixed = (kU + 1.2e-7 + 1.6e-7) + (5.2e-7 + 1.0e-7 + kElPolyErr);            // rad
+constexpr double kElFixedGeneral = (kU + 1.2e-7 + 1.6e-7) + (5.2e-7 + 1.2e-7 + 0.9e-7 + kAzPolyErr + 1.0e-7);   // general path: rho = rho^2 * rsq, min * rcp(max), azimuth polynomial, pi/2 fix-up
+constexpr double kRangeRel = 1.1e-6;
+
 __host__ inline FastCfg make_fast_cfg(int rows, int cols, float vfov, float hfov, int empty_scan_shortcut) {
     FastCfg f;
     const double kPi = 3.14159265358979323846;
@@ -43,11 +76,19 @@ __host__ inline FastCfg make_fast_cfg(int rows, int cols, float vfov, float hfov
     const double ppr_r = (double)rows * 180.0 / (kPi * (double)vfov);
     f.col_scale = (float)ppr_c; f.col_off = 0.5f * (float)cols;
     f.row_scale = (float)ppr_r; f.row_off = 0.5f * (float)rows;
-    f.m_col_a = (float)(ppr_c * 1.2e-6 + (double)cols * 4.0e-7);
-    f.m_col_b = (float)(ppr_c * 1.2e-6);
-    f.m_row = (float)(ppr_r * 2.4e-6 + (double)rows * 4.0e-7);
-    f.m_r_rel = 2.0e-6f; f.m_r_abs = 5.0e-6f;
+    // short elevation path: an elevation of +-atan(0.5) must land at least one full pixel outside the image, so that clamping t = qz / rho
+    // to +-0.5 cannot move a point across a row boundary
+    const double half_v = 0.5 * (double)vfov * kPi / 180.0;
+    f.el_direct = (std::atan(0.5) - half_v) * ppr_r >= 1.0 ? 1 : 0;
+    f.m_col_a = (float)(kMarginSafety * (ppr_c * kAzFixed + (double)cols * 3.5 * kU));
+    f.m_col_b = (float)(kMarginSafety * ppr_c * kAzPerRhoInvR);
+    f.m_row = (float)(kMarginSafety * (ppr_r * (f.el_direct ? kElFixed : kElFixedGeneral) + (double)rows * 4.5 * kU));
+    f.m_r_rel = (float)(kMarginSafety * kRangeRel); f.m_r_abs = 5.0e-6f;
     f.empty_scan_shortcut = empty_scan_shortcut;
+    f.lim_c = 0.5f - f.m_col_a; f.lim_r = 0.5f - f.m_row;
+    f.rel_m1 = f.m_r_rel - 1.0f;
+    f.mr2_rel = 2.0f * f.m_r_rel; f.mr2_abs = 2.0f * f.m_r_abs;
+    f.neg_row_scale = -f.row_scale;
     return f;
 }
 
@@ -55,29 +96,39 @@ __host__ inline FastCfg make_fast_cfg(int rows, int cols, float vfov, float hfov
 LTR_DEV float mufu_rsq(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 LTR_DEV float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// atan(a) for a in [0, 1]: a * P(a^2), degree-8 least-squares/Chebyshev fit, |err| <= 1.1e-7 in f32 Horner form
+// atan(a) for a in [0, 1]: a * P(a^2), 7 coefficients (near-minimax fit of atan(sqrt(z)) / sqrt(z) on [0, 1]); the error constant
+// kAzPolyErr is asserted over every float of [0, 1] by tests/test_gpu_fastpath.py::test_atan_polynomials_exhaustive
 LTR_DEV float fast_atan01(float a) {
     const float z = __fmul_rn(a, a);
-    float p = 0.0028340641874819994f;
-    p = __fmaf_rn(p, z, -0.016005029901862144f);
-    p = __fmaf_rn(p, z, 0.042587608098983765f);
-    p = __fmaf_rn(p, z, -0.07495445758104324f);
-    p = __fmaf_rn(p, z, 0.10636754333972931f);
-    p = __fmaf_rn(p, z, -0.14202570915222168f);
-    p = __fmaf_rn(p, z, 0.19992484152317047f);
-    p = __fmaf_rn(p, z, -0.3333306610584259f);
-    p = __fmaf_rn(p, z, 1.0f);
+    float p = 0.008006718009710312f;
+    p = __fmaf_rn(p, z, -0.037442438304424286f);
+    p = __fmaf_rn(p, z, 0.0843534842133522f);
+    p = __fmaf_rn(p, z, -0.1351214498281479f);
+    p = __fmaf_rn(p, z, 0.1988731473684311f);
+    p = __fmaf_rn(p, z, -0.3332701325416565f);
+    p = __fmaf_rn(p, z, 0.9999994039535522f);
     return __fmul_rn(p, a);
+}
+
+// atan(t) for |t| <= 0.5: t * P(t^2), 5 coefficients (fit on z in [0, 0.25]); odd in t, so the sign comes for free
+LTR_DEV float fast_atan_half(float t) {
+    const float z = __fmul_rn(t, t);
+    float p = 0.06964161992073059f;
+    p = __fmaf_rn(p, z, -0.13479125499725342f);
+    p = __fmaf_rn(p, z, 0.199324369430542f);
+    p = __fmaf_rn(p, z, -0.33331313729286194f);
+    p = __fmaf_rn(p, z, 0.9999998807907104f);
+    return __fmul_rn(p, t);
 }
 
 struct FastProj { float az, el, r, rho_inv_r; };  // rho_inv_r = r / rho
 
-// approximate cart2sph of a point in the sensor frame
+// approximate cart2sph of a point in the sensor frame.  kElDirect: elevation from t = qz / rho clamped to +-0.5 (FastCfg::el_direct).
+template <bool kElDirect = false>
 LTR_DEV FastProj fast_sph(float qx, float qy, float qz) {
     const float rho2 = __fmaf_rn(qy, qy, __fmul_rn(qx, qx));
     const float r2 = __fmaf_rn(qz, qz, rho2);
     const float irho = mufu_rsq(rho2), ir = mufu_rsq(r2);
-    const float rho = __fmul_rn(rho2, irho);
     FastProj o;
     o.r = __fmul_rn(r2, ir);
     o.rho_inv_r = __fmul_rn(o.r, irho);
@@ -90,7 +141,13 @@ LTR_DEV FastProj fast_sph(float qx, float qy, float qz) {
         o.az = copysignf(t, qy);
     }
     // elevation = atan2(qz, rho), rho >= 0
-    {
+    if (kElDirect) {
+        // beyond +-atan(0.5) the row index is clamped anyway (make_fast_cfg checked the room); fminf / fmaxf drop a NaN of qz * irho
+        // (rho == 0), but then the azimuth above is NaN as well and the pair goes to the exact path
+        const float t = fminf(fmaxf(__fmul_rn(qz, irho), -0.5f), 0.5f);
+        o.el = fast_atan_half(t);
+    } else {
+        const float rho = __fmul_rn(rho2, irho);
         const float az_ = fabsf(qz);
         float t = fast_atan01(__fmul_rn(fminf(rho, az_), mufu_rcp(fmaxf(rho, az_))));
         if (az_ > rho) t = __fsub_rn(1.57079632679f, t);
@@ -100,12 +157,13 @@ LTR_DEV FastProj fast_sph(float qx, float qy, float qz) {
 }
 
 // kf: A[0..8], c_hi[9..11], t_lo[12..14] = A * c_lo, ok[15]:  q ~= A * (p - c_hi) - t_lo
+template <bool kElDirect = false>
 LTR_DEV FastProj fast_project(const float* __restrict__ kf, float x, float y, float z) {
     const float dx = __fsub_rn(x, kf[9]), dy = __fsub_rn(y, kf[10]), dz = __fsub_rn(z, kf[11]);
     const float qx = __fmaf_rn(kf[2], dz, __fmaf_rn(kf[1], dy, __fmaf_rn(kf[0], dx, -kf[12])));
     const float qy = __fmaf_rn(kf[5], dz, __fmaf_rn(kf[4], dy, __fmaf_rn(kf[3], dx, -kf[13])));
     const float qz = __fmaf_rn(kf[8], dz, __fmaf_rn(kf[7], dy, __fmaf_rn(kf[6], dx, -kf[14])));
-    return fast_sph(qx, qy, qz);
+    return fast_sph<kElDirect>(qx, qy, qz);
 }
 
 // Rounds a pre-round pixel coordinate when that is certain: returns true and the clamped index iff every value within
@@ -175,41 +233,46 @@ __device__ __noinline__ void exact_full_pair(const PtrView& map, uint64_t e, con
 namespace ltr {
 
 constexpr int kFastThreads = 256;
-constexpr int kFastPts = 4;      // map points per thread (registers), strided by the block size for coalescing
+constexpr int kFastCtasPerSm = 3;   // 85 registers per thread: the per-keyframe and image constants stay in registers across the 4 points of a step
+constexpr int kFastPts = 4;      // map points per thread (registers); lane l of a warp holds points tile * 128 + 32 j + l
 constexpr int kQueueCap = 160;   // per warp and kind: < 32 left over + 4 * 32 pushed per keyframe step
+constexpr int kFastMaxBatch = 32;   // keyframes per launch: their constants travel as a kernel parameter (constant bank)
 
-// `approx_min` (u32 per pixel, float bits, initialised to +inf): running minimum of the APPROXIMATE ranges of the pairs
-// that were queued for pixel px.  A pair whose approximate range exceeds it by more than twice the range margin is
-// provably farther than an already-queued pair and cannot win the pixel, so it is dropped without exact arithmetic.
+// Per-keyframe constants of one launch, passed BY VALUE: the kernel reads them from the constant bank with warp-uniform addresses, so
+// they live in uniform registers / constant operands of the FFMAs instead of 16 vector registers and 4 shared-memory loads per step.
+struct KfBatch { float kf[kFastMaxBatch][16]; };
+
+// `test_img` (u32 per pixel, float bits):
+//   kCandidatesOnly: the scan range image with "no return" pixels replaced by -inf when FastCfg::empty_scan_shortcut (built by
+//       scan_test_image_kernel): a pair can only matter if  scan - range > thres  for SOME range within the margin.
+//   otherwise: the running minimum `approx_min` itself.
+// `approx_min` (u32 per pixel, float bits, initialised to +inf): running minimum of the APPROXIMATE ranges of the pairs that were queued
+// for the pixel.  A pair whose approximate range exceeds it by more than twice the range margin is provably farther than an
+// already-queued pair and cannot win the pixel, so it is dropped without exact arithmetic.
 //
-// Hot loop budget (ncu, r01): the kernel is issue-bound, so the common "no effect" path is kept branch-free: one
-// gather from the scan image (HD/PD) or from approx_min (ND / visible points), compare, done.  Rare pairs reserve a
-// queue slot with a shared-memory atomic (no ballots on the common path).
-template <bool kCandidatesOnly>
-__global__ void __launch_bounds__(kFastThreads, 4) map_project_fast_kernel(PtrView map, const float* __restrict__ kf_fast, const double* __restrict__ poses,
+// Hot loop (profiles/r02_sass_map_project_fast.md): the kernel is issue-bound, so the common "no effect" path is one straight line
+// per point -- transform (12), azimuth (16), ranges (7), elevation (10), pixel + certainty (14), one gather + compare (5) -- and
+// rare pairs reserve a queue slot with a shared-memory atomic (no ballots on the common path).
+template <bool kCandidatesOnly, bool kElDirect>
+__global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) map_project_fast_kernel(PtrView map, const __grid_constant__ KfBatch kb, const double* __restrict__ poses,
                                                                         int kf0, int nb, const double* __restrict__ ext, int ext_identity, int order,
-                                                                        ImgShape g, FastCfg fc, const uint32_t* __restrict__ scan_rimg, float thres,
+                                                                        ImgShape g, const __grid_constant__ FastCfg fc, const uint32_t* __restrict__ scan_rimg,
+                                                                        const uint32_t* __restrict__ test_img, float thres,
                                                                         uint64_t* __restrict__ win, uint32_t* __restrict__ approx_min,
                                                                         CullArgs ca, unsigned long long* __restrict__ counters,
                                                                         unsigned int* __restrict__ work_counter) {
-    extern __shared__ float s_dyn[];
-    float* s_kf = s_dyn;                                                                    // nb * 16
+    extern __shared__ uint64_t s_queues[];
     const int warp = threadIdx.x >> 5;
-    uint64_t* s_qa = (uint64_t*)(s_dyn + ((nb * 16 + 3) & ~3)) + warp * (2 * kQueueCap);
+    uint64_t* s_qa = s_queues + warp * (2 * kQueueCap);
     uint64_t* s_qb = s_qa + kQueueCap;
     __shared__ int s_cnt[kFastThreads / 32][2];
-    for (int t = threadIdx.x; t < nb * 16; t += blockDim.x) s_kf[t] = kf_fast[(size_t)kf0 * 16 + t];
     if ((threadIdx.x & 31) < 2) s_cnt[warp][threadIdx.x & 31] = 0;
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
     const uint32_t npx = (uint32_t)(g.rows * g.cols);
     const int hi_c = g.cols - 1, hi_r = g.rows - 1;
-    // folded constants
-    const float kMagic = 12582912.0f;
-    const float lim_c = 0.5f - fc.m_col_a, lim_r = 0.5f - fc.m_row;
-    const float thr_lo = thres - fc.m_r_abs, rel_m1 = fc.m_r_rel - 1.0f;
-    const float mr2_rel = 2.0f * fc.m_r_rel, mr2_abs = 2.0f * fc.m_r_abs;
-    const uint32_t empty_bits = fc.empty_scan_shortcut ? 0xff800000u : kNoPointBitsF;
+    const float kMagic = 12582912.0f;            // 1.5 * 2^23: v + kMagic has the nearest integer in its low mantissa bits
+    const float thr_lo = thres - fc.m_r_abs;
     unsigned n_a = 0, n_b = 0, n_atomics = 0, n_culled = 0;
     // Persistent warps: each warp claims 128-point tiles from a global counter until the map is exhausted, so warps whose
     // tiles are culled in many keyframes do not leave issue slots idle while their CTA-mates finish.
@@ -220,15 +283,12 @@ __global__ void __launch_bounds__(kFastThreads, 4) map_project_fast_kernel(PtrVi
     tile_u = __shfl_sync(0xffffffffu, tile_u, 0);
     const long long tile = (long long)tile_u;
     if (tile >= total_tiles) break;
-    // lane l holds points tile * 128 + 32 j + l, j = 0..3 (coalesced per j)
     const int64_t base = (int64_t)tile * (32 * kFastPts) + lane;
     float px_[kFastPts], py_[kFastPts], pz_[kFastPts];
-    uint32_t pi_[kFastPts];
 #pragma unroll
     for (int j = 0; j < kFastPts; ++j) {
         // the last tile re-processes point n-1 in its padding lanes: harmless (atomicMin of an identical key)
         const int64_t i = min(base + (int64_t)j * 32, map.n - 1);
-        pi_[j] = (uint32_t)i;
         px_[j] = map.x[i]; py_[j] = map.y[i]; pz_[j] = map.z[i];
     }
     // Tile culling (project_cull.cuh): lane l tests this 128-point tile against keyframe l of the launch; the ballot is the
@@ -236,72 +296,79 @@ __global__ void __launch_bounds__(kFastThreads, 4) map_project_fast_kernel(PtrVi
     unsigned cull_mask = 0u;
     if (kCandidatesOnly && ca.enabled) {
         const float4 t = ca.tiles[tile];
-        const bool c = ((int)lane < nb) && tile_culled(s_kf + 16 * lane, t, fc, g, ca, (int)lane, thres);
+        const bool c = ((int)lane < nb) && tile_culled(kb.kf[lane], t, fc, g, ca, (int)lane, thres);
         cull_mask = __ballot_sync(0xffffffffu, c);
         if (lane == 0) n_culled += __popc(cull_mask);
     }
-    for (int k = 0; k < nb; ++k) {
-        if ((cull_mask >> k) & 1u) continue;   // warp-uniform
-        float kf[16];
-        {
-            const float4* s4 = reinterpret_cast<const float4*>(s_kf + 16 * k);
-            const float4 a = s4[0], b = s4[1], c = s4[2], d = s4[3];
-            kf[0] = a.x; kf[1] = a.y; kf[2] = a.z; kf[3] = a.w; kf[4] = b.x; kf[5] = b.y; kf[6] = b.z; kf[7] = b.w;
-            kf[8] = c.x; kf[9] = c.y; kf[10] = c.z; kf[11] = c.w; kf[12] = d.x; kf[13] = d.y; kf[14] = d.z; kf[15] = d.w;
-        }
-        const bool kf_ok = kf[15] != 0.0f;  // warp-uniform
-        const uint32_t kbase = (uint32_t)k * npx;   // 32-bit pixel offsets: nb * npx < 2^31 (checked by the host)
+    for (int k = 0; k < nb; ++k) {                    // a plain counted loop: k stays provably warp-uniform, so kb.kf[k] is read with LDCU
+        if ((cull_mask >> k) & 1u) continue;         // warp-uniform (ballot)
+        const float* __restrict__ kf = kb.kf[k];
+        const bool kf_ok = kf[15] != 0.0f;
+        const uint32_t* __restrict__ test_k = test_img + (size_t)k * npx;    // this keyframe's images
+        uint32_t* __restrict__ amin_k = approx_min + (size_t)k * npx;
+        // Phase 1, branch-free: project the thread's points and ISSUE all their image gathers, so that the (mostly L2) latencies of
+        // the four loads overlap instead of being paid one after the other behind a branch each.
+        float fr_[kFastPts], tv_[kFastPts];
+        uint32_t pxl_[kFastPts];
+        bool certain_[kFastPts];
 #pragma unroll
         for (int j = 0; j < kFastPts; ++j) {
-            const FastProj f = fast_project(kf, px_[j], py_[j], pz_[j]);
+            const FastProj f = fast_project<kElDirect>(kf, px_[j], py_[j], pz_[j]);
             const float vcol = __fmaf_rn(f.az, fc.col_scale, fc.col_off);
-            const float vrow = __fmaf_rn(-f.el, fc.row_scale, fc.row_off);
+            const float vrow = __fmaf_rn(f.el, fc.neg_row_scale, fc.row_off);
             const float yc = __fadd_rn(vcol, kMagic), yr = __fadd_rn(vrow, kMagic);
-            const float dc = fabsf(__fsub_rn(vcol, __fsub_rn(yc, kMagic)));   // distance to the nearest integer
+            const float dc = fabsf(__fsub_rn(vcol, __fsub_rn(yc, kMagic)));   // distance to the nearest integer (NaN stays NaN)
             const float dr = fabsf(__fsub_rn(vrow, __fsub_rn(yr, kMagic)));
-            const int c = min(max(__float_as_int(yc) - 0x4B400000, 0), hi_c);
+            const int c = min(max(__float_as_int(yc) - 0x4B400000, 0), hi_c);   // NaN -> some in-range pixel; such a pair is never "certain"
             const int r = min(max(__float_as_int(yr) - 0x4B400000, 0), hi_r);
             // certain <=> both coordinates are farther than their margin from a rounding boundary (false for NaN)
-            const bool certain = kf_ok & (__fmaf_rn(fc.m_col_b, f.rho_inv_r, dc) < lim_c) & (dr < lim_r);
-            const uint32_t pxl = (uint32_t)(r * g.cols + c);
-            const uint32_t idx = kbase + pxl;
-            if (certain) {
-                bool maybe = true;
-                if (kCandidatesOnly) {
-                    uint32_t sb = scan_rimg[idx];
-                    if (sb == kNoPointBitsF) sb = empty_bits;   // -inf when pixels without a scan return can never flag
-                    // candidate for SOME range within the margin: scan - range > thres   (sr - r + m_rel r >= thres - m_abs)
-                    maybe = !(__fmaf_rn(f.r, rel_m1, __uint_as_float(sb)) < thr_lo);
-                }
+            certain_[j] = kf_ok & (__fmaf_rn(fc.m_col_b, f.rho_inv_r, dc) < fc.lim_c) & (dr < fc.lim_r);
+            pxl_[j] = (uint32_t)(r * g.cols + c);
+            fr_[j] = f.r;
+            tv_[j] = __uint_as_float(test_k[pxl_[j]]);      // unconditional: the index is always inside the image
+        }
+        // Phase 2: decide.  Almost every pair ends at the first comparison.
+#pragma unroll
+        for (int j = 0; j < kFastPts; ++j) {
+            const float fr = fr_[j], tv = tv_[j];
+            const uint32_t pxl = pxl_[j];
+            if (certain_[j]) {
+                bool maybe;
+                if (kCandidatesOnly) maybe = !(__fmaf_rn(fr, fc.rel_m1, tv) < thr_lo);   // scan - r + m_rel r >= thres - m_abs for some range within the margin
+                else maybe = !(fr > __fadd_rn(tv, __fmaf_rn(fc.mr2_rel, fr, fc.mr2_abs)));   // not provably farther than an already-queued pair
                 if (maybe) {
-                    const float cur = __uint_as_float(approx_min[idx]);
-                    if (!(f.r > __fadd_rn(cur, __fmaf_rn(mr2_rel, f.r, mr2_abs)))) {   // not provably farther than an already-queued pair
-                        if (f.r < cur) atomicMin(&approx_min[idx], __float_as_uint(f.r));
-                        s_qa[atomicAdd(&s_cnt[warp][0], 1)] = q_pack(pi_[j], pxl, (uint32_t)k);
-                    }
+                    bool push = true;
+                    if (kCandidatesOnly) {
+                        const float cur = __uint_as_float(amin_k[pxl]);
+                        push = !(fr > __fadd_rn(cur, __fmaf_rn(fc.mr2_rel, fr, fc.mr2_abs)));
+                        if (push && fr < cur) atomicMin(&amin_k[pxl], __float_as_uint(fr));
+                    } else if (fr < tv) atomicMin(&amin_k[pxl], __float_as_uint(fr));
+                    if (push) s_qa[atomicAdd(&s_cnt[warp][0], 1)] = q_pack((uint32_t)(base + j * 32 < map.n ? base + j * 32 : map.n - 1), pxl, (uint32_t)k);
                 }
             } else {
-                s_qb[atomicAdd(&s_cnt[warp][1], 1)] = q_pack(pi_[j], 0u, (uint32_t)k);
+                s_qb[atomicAdd(&s_cnt[warp][1], 1)] = q_pack((uint32_t)(base + j * 32 < map.n ? base + j * 32 : map.n - 1), 0u, (uint32_t)k);
             }
         }
         __syncwarp();
         int qa = *(volatile int*)&s_cnt[warp][0];
-        while (qa >= 32) {
-            qa -= 32;
-            const uint64_t e = s_qa[qa + lane];
-            exact_range_pair<kCandidatesOnly>(map, e, poses, kf0, ext, ext_identity, order, npx, scan_rimg, thres, win, fc.empty_scan_shortcut, &n_atomics);
-            ++n_a;
-        }
         int qb = *(volatile int*)&s_cnt[warp][1];
-        while (qb >= 32) {
-            qb -= 32;
-            const uint64_t e = s_qb[qb + lane];
-            exact_full_pair<kCandidatesOnly>(map, e, poses, kf0, ext, ext_identity, order, g, scan_rimg, thres, win, fc.empty_scan_shortcut, &n_atomics);
-            ++n_b;
+        if ((qa | qb) >= 32) {   // warp-uniform
+            while (qa >= 32) {
+                qa -= 32;
+                const uint64_t e = s_qa[qa + lane];
+                exact_range_pair<kCandidatesOnly>(map, e, poses, kf0, ext, ext_identity, order, npx, scan_rimg, thres, win, fc.empty_scan_shortcut, &n_atomics);
+                ++n_a;
+            }
+            while (qb >= 32) {
+                qb -= 32;
+                const uint64_t e = s_qb[qb + lane];
+                exact_full_pair<kCandidatesOnly>(map, e, poses, kf0, ext, ext_identity, order, g, scan_rimg, thres, win, fc.empty_scan_shortcut, &n_atomics);
+                ++n_b;
+            }
+            __syncwarp();
+            if (lane == 0) { s_cnt[warp][0] = qa; s_cnt[warp][1] = qb; }
+            __syncwarp();
         }
-        __syncwarp();
-        if (lane == 0) { s_cnt[warp][0] = qa; s_cnt[warp][1] = qb; }
-        __syncwarp();
     }
     }  // persistent tile loop
     const int qa = *(volatile int*)&s_cnt[warp][0], qb = *(volatile int*)&s_cnt[warp][1];

@@ -1,8 +1,6 @@
 // libltr_b200.so -- order-preserving compaction, reductions, voxel centroid, merge and pre-clean kernels.
 #include "ltr_internal.cuh"
 #include "ref_math.cuh"
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 #include <cfloat>
 #include <cmath>
 #include <algorithm>
@@ -57,7 +55,7 @@ __global__ void __launch_bounds__(kPartThreads) part_count_kernel(const uint8_t*
 }
 
 // single-block exclusive scan of up to 2^31 total over nb block counts; writes total to out[nb]
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int nb) {
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t* in, uint32_t* out, int nb)   /* in may alias out */ {
     __shared__ int s_warp[33];
     __shared__ uint32_t s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -158,15 +156,175 @@ int count_flags(ltr_ctx* ctx, const uint8_t* flags, int64_t n, int64_t* count) {
     return LTR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Device-wide exclusive prefix sum of u32 (reduce - scan - apply; in and out may alias).  Used for the kNN grid's cell starts,
+// the voxel ranks and the digit offsets of the radix sort below.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ part) {
+    __shared__ uint32_t s_warp[32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int r = 0; r < kScanItems; ++r) {
+        const int64_t i = base + (int64_t)r * kScanThreads + threadIdx.x;
+        if (i < n) sum += in[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        sum = s_warp[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+        if (threadIdx.x == 0) part[blockIdx.x] = sum;
+    }
+}
+
+// each thread owns kScanItems CONSECUTIVE elements (blocked arrangement), so the scan order is the element order
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* in, uint32_t* out, int64_t n,   /* in may alias out */
+                                                                  const uint32_t* __restrict__ part_excl) {
+    __shared__ uint32_t s_warp[33];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int r = 0; r < kScanItems; ++r) { const int64_t i = base + r; v[r] = i < n ? in[i] : 0u; sum += v[r]; }
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if ((int)lane >= o) wi += t; }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = part_excl[blockIdx.x] + s_warp[warp] + incl - sum;
+#pragma unroll
+    for (int r = 0; r < kScanItems; ++r) { const int64_t i = base + r; if (i < n) out[i] = run; run += v[r]; }
+}
+
 int exclusive_scan_u32(ltr_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n) {
-    size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, n, ctx->stream);
-    void* tmp = nullptr;
-    ScratchGuard g_tmp(ctx, &tmp);
-    LTR_TRY(dev_alloc(ctx, &tmp, tmp_bytes));
-    LTR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, n, ctx->stream));
-    ctx->launches += 2;
-    g_tmp.release();
+    if (n <= 0) return LTR_OK;
+    const int nb = (int)((n + kScanTile - 1) / kScanTile);
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
+    LTR_TRY(dev_alloc(ctx, &p, (size_t)(2 * nb + 2) * sizeof(uint32_t)));
+    uint32_t* part = (uint32_t*)p;
+    uint32_t* part_excl = part + nb;
+    scan_reduce_kernel<<<nb, kScanThreads, 0, ctx->stream>>>(in, n, part);
+    LTR_LAUNCH_CHECK(ctx);
+    scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(part, part_excl, nb);
+    LTR_LAUNCH_CHECK(ctx);
+    scan_apply_kernel<<<nb, kScanThreads, 0, ctx->stream>>>(in, out, n, part_excl);
+    LTR_LAUNCH_CHECK(ctx);
+    g_p.release();
+    return LTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stable LSD radix sort of (u64 key, u32 value) pairs on the key bits [0, key_bits), 8 bits per pass (the voxeliser's Morton sort).
+// Per pass: per-tile digit histogram -> exclusive scan of the digit-major [256][tiles] matrix -> stable scatter.  Stability inside a
+// tile: every warp owns a CONTIGUOUS run of the tile and walks it 32 elements at a time; __match_any_sync gives each element its rank
+// among the equal digits of its row, per-warp running counters give the rank among the earlier rows, and a prefix over the warps of
+// the tile gives the rank among the earlier warps.  Equal keys therefore keep their input order, which is what makes the voxel
+// sums run in insertion order (PCL's leaf containers accumulate in insertion order).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRsThreads = 256;
+constexpr int kRsItems = 16;
+constexpr int kRsTile = kRsThreads * kRsItems;   // 4096 keys per tile, 512 per warp
+
+__global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist, int ntiles) {
+    __shared__ uint32_t s_hist[256];
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kRsTile;
+#pragma unroll 4
+    for (int r = 0; r < kRsItems; ++r) {
+        const int64_t i = base + (int64_t)r * kRsThreads + threadIdx.x;
+        if (i < n) atomicAdd(&s_hist[(unsigned)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = s_hist[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
+                                                                const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int64_t n, int shift,
+                                                                const uint32_t* __restrict__ offs, int ntiles) {
+    __shared__ uint32_t s_cnt[kRsThreads / 32][256];
+    __shared__ uint32_t s_base[256];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = threadIdx.x; t < (kRsThreads / 32) * 256; t += kRsThreads) (&s_cnt[0][0])[t] = 0;
+    __syncthreads();
+    const int64_t chunk = (int64_t)blockIdx.x * kRsTile + (int64_t)warp * (32 * kRsItems);
+    uint64_t key[kRsItems];
+    uint32_t rank[kRsItems];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const int64_t i = chunk + r * 32 + lane;
+        const bool valid = i < n;
+        key[r] = valid ? keys_in[i] : 0ull;
+        const unsigned d = (unsigned)(key[r] >> shift) & 255u;
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : (256u + lane));   // padding lanes match nobody
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if ((int)lane == leader && valid) { old = s_cnt[warp][d]; s_cnt[warp][d] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = old + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // exclusive prefix over the warps of the tile, one digit per thread; and the tile's global base per digit
+        const int d = threadIdx.x;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w = 0; w < kRsThreads / 32; ++w) { const uint32_t c = s_cnt[w][d]; s_cnt[w][d] = sum; sum += c; }
+        s_base[d] = offs[(size_t)d * ntiles + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const int64_t i = chunk + r * 32 + lane;
+        if (i < n) {
+            const unsigned d = (unsigned)(key[r] >> shift) & 255u;
+            const uint32_t pos = s_base[d] + s_cnt[warp][d] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = vals_in[i];
+        }
+    }
+}
+
+// Sorts (keys0, vals0) using (keys1, vals1) as the other half of the ping-pong; *keys_sorted / *vals_sorted point at the result.
+static int radix_sort_pairs(ltr_ctx* ctx, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, int64_t n, int key_bits,
+                            uint64_t** keys_sorted, uint32_t** vals_sorted) {
+    *keys_sorted = keys0; *vals_sorted = vals0;
+    if (n <= 1 || key_bits <= 0) return LTR_OK;
+    const int ntiles = (int)((n + kRsTile - 1) / kRsTile);
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
+    LTR_TRY(dev_alloc(ctx, &p, ((size_t)256 * ntiles + 1) * sizeof(uint32_t)));
+    uint32_t* hist = (uint32_t*)p;
+    uint64_t *kin = keys0, *kout = keys1;
+    uint32_t *vin = vals0, *vout = vals1;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        rs_hist_kernel<<<ntiles, kRsThreads, 0, ctx->stream>>>(kin, n, shift, hist, ntiles);
+        LTR_LAUNCH_CHECK(ctx);
+        if ((int64_t)256 * ntiles <= 1024 * 64) {   // small matrix: one block scans it (also writes the total past the end, hence the + 1 above)
+            scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(hist, hist, 256 * ntiles);
+            LTR_LAUNCH_CHECK(ctx);
+        } else LTR_TRY(exclusive_scan_u32(ctx, hist, hist, (int64_t)256 * ntiles));
+        rs_scatter_kernel<<<ntiles, kRsThreads, 0, ctx->stream>>>(kin, kout, vin, vout, n, shift, hist, ntiles);
+        LTR_LAUNCH_CHECK(ctx);
+        std::swap(kin, kout); std::swap(vin, vout);
+    }
+    g_p.release();
+    *keys_sorted = kin; *vals_sorted = vin;
     return LTR_OK;
 }
 
@@ -387,18 +545,12 @@ static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out)
             return LTR_OK;
         }
     }
-    size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys0, keys1, idx0, idx1, (int)n, 0, 3 * b.depth, ctx->stream);
-    void* tmp = nullptr;
-    ScratchGuard g_tmp(ctx, &tmp);
-    LTR_TRY(dev_alloc(ctx, &tmp, tmp_bytes));
-    LTR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys0, keys1, idx0, idx1, (int)n, 0, 3 * b.depth, ctx->stream));
-    ctx->launches += (3 * b.depth + 7) / 8 + 1;
-    g_tmp.release();
-    vox_head_kernel<<<nb, T, 0, ctx->stream>>>(keys1, n, head);
+    uint64_t* keys_s; uint32_t* idx_s;
+    LTR_TRY(radix_sort_pairs(ctx, keys0, keys1, idx0, idx1, n, 3 * b.depth, &keys_s, &idx_s));
+    vox_head_kernel<<<nb, T, 0, ctx->stream>>>(keys_s, n, head);
     LTR_LAUNCH_CHECK(ctx);
     LTR_TRY(exclusive_scan_u32(ctx, head, rank, n));
-    vox_centroid_kernel<<<nb, T, 0, ctx->stream>>>(v, keys1, idx1, head, rank, n, *out);
+    vox_centroid_kernel<<<nb, T, 0, ctx->stream>>>(v, keys_s, idx_s, head, rank, n, *out);
     LTR_LAUNCH_CHECK(ctx);
     uint32_t last[2];
     unsigned int hbad = 0;
@@ -583,6 +735,7 @@ int ltr_preclean(ltr_ctx* ctx, ltr_scanset scans, float radius, ltr_scanset* out
 }
 
 int ltr_flags_device_ptr(ltr_ctx* ctx, ltr_cloud map, uint8_t** flags, int64_t* n) {
+    ApiTrace tr__(ctx, "ltr_flags_device_ptr");
     DevCloud* c;
     LTR_TRY(cloud_get(ctx, map, &c));
     LTR_TRY(cloud_ensure_flags(ctx, c));
@@ -591,6 +744,7 @@ int ltr_flags_device_ptr(ltr_ctx* ctx, ltr_cloud map, uint8_t** flags, int64_t* 
     return LTR_OK;
 }
 int ltr_flags_download(ltr_ctx* ctx, ltr_cloud map, uint8_t* flags, int64_t capacity) {
+    ApiTrace tr__(ctx, "ltr_flags_download");
     DevCloud* c;
     LTR_TRY(cloud_get(ctx, map, &c));
     LTR_TRY(cloud_ensure_flags(ctx, c));
@@ -600,6 +754,7 @@ int ltr_flags_download(ltr_ctx* ctx, ltr_cloud map, uint8_t* flags, int64_t capa
     return LTR_OK;
 }
 int ltr_flags_upload(ltr_ctx* ctx, ltr_cloud map, const uint8_t* flags, int64_t n) {
+    ApiTrace tr__(ctx, "ltr_flags_upload");
     DevCloud* c;
     LTR_TRY(cloud_get(ctx, map, &c));
     if (n != c->n) return fail(ctx, LTR_ERR_INVALID, "flag count %lld != map size %lld", (long long)n, (long long)c->n);

@@ -40,7 +40,7 @@ class Comm(ctypes.Structure):
                 ("allreduce_max_u8", _ALLREDUCE), ("allgather_i64", _ALLGATHER_I64), ("allgatherv_f32", _ALLGATHERV)]
 
 
-HOST_EXPORTS = ["ltrh_params_default", "ltrh_create", "ltrh_destroy", "ltrh_last_error", "ltrh_set_comm", "ltrh_context",
+HOST_EXPORTS = ["ltrh_params_default", "ltrh_create", "ltrh_destroy", "ltrh_last_error", "ltrh_set_comm", "ltrh_context", "ltrh_comm_init_nccl", "ltrh_owns_session",
                 "ltrh_load_session", "ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0", "ltrh_cascade_promote_updated", "ltrh_stage", "ltrh_cloud",
                 "ltrh_scanset", "ltrh_timing", "ltrh_log_count", "ltrh_log_get", "ltrh_io_last_error", "ltrh_io_read_pcd", "ltrh_io_write_pcd",
                 "ltrh_io_read_poses", "ltrh_io_parse_keyframes", "ltrh_io_parse_keyframes_in_roi", "ltrh_io_voxel_grid", "ltrh_io_yaml_get"]
@@ -66,6 +66,8 @@ def host_lib():
     L.ltrh_set_comm.argtypes = [vp, P(Comm)]
     L.ltrh_context.argtypes = [vp]
     L.ltrh_context.restype = vp
+    L.ltrh_comm_init_nccl.argtypes = [vp, vp, i32, i32, i32]
+    L.ltrh_owns_session.argtypes = [vp, i32]
     L.ltrh_load_session.argtypes = [vp, i32, vp, vp, vp, vp, i32]
     for f in ("ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0", "ltrh_cascade_promote_updated"):
         getattr(L, f).argtypes = [vp]
@@ -188,11 +190,21 @@ class TorchDistComm:
             return 1
 
 
+def nccl_unique_id():
+    """128 bytes of ncclGetUniqueId (call on ONE rank, hand the bytes to the others through the launcher's own channel)."""
+    buf = ctypes.create_string_buffer(128)
+    rc = binding.lib().ltr_nccl_unique_id(buf)
+    if rc != 0:
+        raise binding.LtrError(rc, binding.lib().ltr_last_error(None).decode())
+    return bytes(buf.raw)
+
+
 def selfremovert_schedule(resolutions):
-    """Removerter::selfRemovert (Removerter.cpp:1378-1393): remove(r), revert(0.95 r), remove(r) per resolution."""
+    """Removerter::selfRemovert (Removerter.cpp:1378-1393): remove(r), revert(0.95 r), remove(r) per resolution.  The revert
+    resolution is `0.95 * _res_alpha` with a float argument, i.e. a DOUBLE product narrowed once when passed on as float (:1385)."""
     s = []
     for r in resolutions:
-        s += [(OP_REMOVE, r), (OP_REVERT, float(np.float32(0.95) * np.float32(r))), (OP_REMOVE, r)]
+        s += [(OP_REMOVE, r), (OP_REVERT, float(np.float32(0.95 * float(np.float32(r))))), (OP_REMOVE, r)]
     return s
 
 
@@ -229,6 +241,16 @@ class Removerter:
         self.ctx = binding.Context.__new__(binding.Context)
         self.ctx._h = ctypes.c_void_p(L.ltrh_context(self._h))
         self.K = [0, 0]
+        self.rank, self.world, self.split = 0, 1, False
+
+    def init_nccl(self, id128, rank, world, split_sessions=True):
+        """Native multi-GPU transport (ltrh_comm_init_nccl): every rank passes the same 128-byte id (nccl_unique_id() of one rank)."""
+        self._ck(host_lib().ltrh_comm_init_nccl(self._h, id128, rank, world, 1 if split_sessions else 0))
+        self.rank, self.world = rank, world
+        self.split = bool(split_sessions) and world >= 2 and world % 2 == 0
+
+    def owns(self, sess):
+        return bool(host_lib().ltrh_owns_session(self._h, sess))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -2,6 +2,9 @@
 // First-party logic pinned against the compiled reference sources (oracle/ref_shim, tests/test_ref_pin.py);
 // PARITY UNPINNED for the third-party semantics restated here (no reference tests exist, see comments).
 #include "oracle.h"
+#ifdef _OPENMP
+#include <parallel/algorithm>
+#endif
 #include <algorithm>
 #include <cfloat>
 #include <chrono>
@@ -231,7 +234,12 @@ int octreeDownsampling(const Cloud& src_in, Cloud& dst, float leaf) {
         if (kx > lim || ky > lim || kz > lim) return -1;
         keyed[i] = std::make_pair(mortonXYZ(kx, ky, kz, b.depth), (uint32_t)i);
     }
-    std::sort(keyed.begin(), keyed.end());  // (code, original index): stable w.r.t. insertion order
+    // (code, original index) pairs are all distinct, so any correct sort gives the same order: stable w.r.t. insertion order
+#ifdef _OPENMP
+    if (n > (size_t)1 << 20) __gnu_parallel::sort(keyed.begin(), keyed.end());
+    else
+#endif
+    std::sort(keyed.begin(), keyed.end());
     size_t i = 0;
     while (i < n) {
         size_t j = i;

@@ -66,6 +66,12 @@ def _lib(omp=False):
         L.ref_extract_knn_diff.argtypes = [vp, ci, ci, vp, i64, ci, f32]
         L.ref_load_session_mem.argtypes = [vp, ci, vp, vp, vp, ci]
         L.ref_saved_get.argtypes = [ci, cp, ci, vp, i64]; L.ref_saved_get.restype = i64
+        f64 = ctypes.c_double
+        L.ref_time_dynamic_idx.argtypes = [vp, ci, ci, ci, ci, ci, vp]; L.ref_time_dynamic_idx.restype = f64
+        L.ref_time_parse_static.argtypes = [vp, ci]; L.ref_time_parse_static.restype = f64
+        L.ref_knn_set_target.argtypes = [vp, ci, vp, i64, ci, f32]; L.ref_knn_set_target.restype = f64
+        L.ref_time_knn_queries.argtypes = [vp, ci, ci, ci, vp]; L.ref_time_knn_queries.restype = f64
+        L.ref_time_merge.argtypes = [vp, ci, cp, vp]; L.ref_time_merge.restype = f64
         _lib_cache[omp] = L
     return _lib_cache[omp]
 
@@ -257,6 +263,26 @@ class Removerter:
         """Session::extractLowDynPointsViaKnnDiff (low) / extractHighDynPointsViaKnnDiff of `sess` against target_xyzi."""
         t = _f32(target_xyzi)
         _lib(self._omp).ref_extract_knn_diff(self._h, sess, int(low), t.ctypes.data, len(t), k, thr)
+
+    # ---- timed per-keyframe loops (bench.py --impl reference) ----
+    def time_dynamic_idx(self, mode, target, source, rows, cols):
+        n = ctypes.c_int64()
+        return _lib(self._omp).ref_time_dynamic_idx(self._h, mode, target, source, rows, cols, ctypes.byref(n)), n.value
+
+    def time_parse_static(self, sess):
+        return _lib(self._omp).ref_time_parse_static(self._h, sess)
+
+    def knn_set_target(self, sess, target_xyzi, k, thr):
+        t = _f32(target_xyzi)
+        return _lib(self._omp).ref_knn_set_target(self._h, sess, t.ctypes.data, len(t), k, thr)
+
+    def time_knn_queries(self, sess, low, omp_cores):
+        n = ctypes.c_int64()
+        return _lib(self._omp).ref_time_knn_queries(self._h, sess, int(low), omp_cores, ctypes.byref(n)), n.value
+
+    def time_merge(self, sess, name):
+        n = ctypes.c_int64()
+        return _lib(self._omp).ref_time_merge(self._h, sess, name.encode(), ctypes.byref(n)), n.value
 
     def scans(self, name, sess=0):
         L = _lib(self._omp)

@@ -4,6 +4,7 @@
 // Built by oracle/Makefile into oracle/_ref/libltremovert_ref.so (git-ignored; travels to the GPU box).
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <ctime>
@@ -336,6 +337,69 @@ int ref_extract_knn_diff(void* h, int sess, int low, const float* target_xyzi, i
     PC::Ptr t = make_cloud(target_xyzi, n);
     if (low) S.extractLowDynPointsViaKnnDiff(t); else S.extractHighDynPointsViaKnnDiff(t);
     return 0;
+}
+
+// ---- timing of the reference's own per-keyframe loops (bench.py --impl reference; see its docstring) ----
+// Each call runs ONE loop of the reference over the keyframes currently loaded in the session(s), on whatever maps the caller put
+// into the members, and returns the seconds spent inside (steady clock around the reference's own member function).
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// mode 0 / 1 / 2 = calcDescrepancyAndParseDynamicPointIdxForEachScan / ...ForND / ...ForPD (Removerter.cpp:542-593, 485-540, 429-482)
+double ref_time_dynamic_idx(void* h, int mode, int target, int source, int rows, int cols, int64_t* n_dynamic) {
+    Removerter* R = (Removerter*)h;
+    Session& t = sess_of(R, target); Session& s = sess_of(R, source);
+    const double t0 = now_s();
+    std::vector<int> v;
+    if (mode == 0) v = R->calcDescrepancyAndParseDynamicPointIdxForEachScan(t, s, {rows, cols});
+    else if (mode == 1) v = R->calcDescrepancyAndParseDynamicPointIdxForEachScanForND(t, s, {rows, cols});
+    else v = R->calcDescrepancyAndParseDynamicPointIdxForEachScanForPD(t, s, {rows, cols});
+    const double dt = now_s() - t0;
+    if (n_dynamic) *n_dynamic = (int64_t)v.size();
+    return dt;
+}
+// Session::parseStaticScansViaProjection (Session.cpp:305-308 -> 348-360) of one session
+double ref_time_parse_static(void* h, int sess) {
+    Session& S = sess_of((Removerter*)h, sess);
+    const double t0 = now_s();
+    S.parseStaticScansViaProjection();
+    return now_s() - t0;
+}
+// kd-tree construction of Session::extract{Low,High}DynPointsViaKnnDiff (Session.cpp:403 / :489), a per-call fixed cost
+double ref_knn_set_target(void* h, int sess, const float* xyzi, int64_t n, int k, float thr) {
+    Session& S = sess_of((Removerter*)h, sess);
+    S.kNumKnnPointsToCompare = k;
+    S.kScanKnnAndMapKnnAvgDiffThreshold = thr;
+    const double t0 = now_s();
+    S.kdtree_target_map_global_->setInputCloud(make_cloud(xyzi, n));
+    return now_s() - t0;
+}
+// the keyframe loop of the same two functions (Session.cpp:408-414 / :491-497, OpenMP over keyframes as in the reference)
+double ref_time_knn_queries(void* h, int sess, int low, int omp_cores, int64_t* n_diff) {
+    Session& S = sess_of((Removerter*)h, sess);
+    const int K = low ? (int)S.keyframe_scans_static_projected_.size() : (int)S.keyframe_scans_.size();
+    std::vector<PC::Ptr> co((size_t)K), di((size_t)K);
+    const double t0 = now_s();
+#pragma omp parallel for num_threads(omp_cores)
+    for (int k = 0; k < K; ++k) {
+        auto pr = low ? S.partitionLowDynamicPointsOfScanByKnn(k) : S.partitionHighDynamicPointsOfScanByKnn(k);
+        co[(size_t)k] = pr.first; di[(size_t)k] = pr.second;
+    }
+    const double dt = now_s() - t0;
+    int64_t nd = 0;
+    for (int k = 0; k < K; ++k) nd += (int64_t)di[(size_t)k]->points.size();
+    if (n_diff) *n_diff = nd;
+    if (low) { S.scans_knn_coexist_ = co; S.scans_knn_diff_ = di; } else S.keyframe_scans_dynamic_ = di;
+    return dt;
+}
+// mergeScansWithinGlobalCoordUtil (utility.cpp:170-192) over one per-keyframe member of the session
+double ref_time_merge(void* h, int sess, const char* name, int64_t* n_out) {
+    Session& S = sess_of((Removerter*)h, sess);
+    std::vector<PC::Ptr>* v = scans_member(S, name);
+    if (!v) return -1.0;
+    const double t0 = now_s();
+    auto m = mergeScansWithinGlobalCoordUtil(*v, S.keyframe_poses_, S.kSE3MatExtrinsicLiDARtoPoseBase);
+    const double dt = now_s() - t0;
+    if (n_out) *n_out = (int64_t)m->points.size();
+    return dt;
 }
 
 // ---- what the run wrote through pcl::io::savePCDFileBinary ----

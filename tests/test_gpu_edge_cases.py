@@ -78,13 +78,33 @@ def test_reference_undefined_behaviour_is_rejected(ctx):
         with pytest.raises(ltr.LtrError) as e:
             ctx.apply_partition(m)
         assert e.value.code == -3
-    # kNN against fewer than k points / an empty target (FLANN refuses to build an empty tree)
+    # kNN against an empty target (PCL asserts on an empty tree)
     ss = ctx.scanset_upload(np.ones((5, 4), np.float32), [0, 5])
     ps = ctx.poses_upload(I4, I4)
-    for tgt in (np.zeros((0, 4), np.float32), np.ones((1, 4), np.float32)):
-        with pytest.raises(ltr.LtrError) as e:
-            ctx.knn_diff(ss, ps, ctx.cloud_upload(tgt), 2, 0.01)
-        assert e.value.code == -3
+    with pytest.raises(ltr.LtrError) as e:
+        ctx.knn_diff(ss, ps, ctx.cloud_upload(np.zeros((0, 4), np.float32)), 2, 0.01)
+    assert e.value.code == -3
+
+
+@pytest.mark.parametrize("n_target,k,thr", [(1, 2, 0.01), (1, 2, 1.0), (2, 3, 0.5), (3, 5, 2.0)])
+def test_knn_target_smaller_than_k(ctx, n_target, k, thr):
+    """Fewer target points than k: PCL's nearestKSearch returns all of them and the reference still divides their sum by k
+    (Session.cpp:470-471, 592-594) -- e.g. a strong-ND map of one point in removeWeakNDMapPointsHavingStrongNDInNear.  The device path
+    must give the oracle's partition, not an error."""
+    rng = np.random.default_rng(5 + n_target)
+    tgt = np.zeros((n_target, 4), np.float32); tgt[:, :3] = rng.uniform(-1, 1, (n_target, 3))
+    q = np.zeros((4000, 4), np.float32); q[:, :3] = rng.uniform(-2, 2, (4000, 3)); q[:, 3] = np.arange(4000)
+    q[:50, :3] = tgt[0, :3] + rng.normal(0, 0.02, (50, 3)).astype(np.float32)
+    ss = ctx.scanset_upload(q, [0, len(q)])
+    ps = ctx.poses_upload(I4, I4)
+    th = ctx.cloud_upload(tgt)
+    co, di = ctx.knn_diff(ss, ps, th, k, thr)
+    lab, eco, edi = oracle.knn_partition(q, I4[0] if I4.ndim == 3 else I4, I4[0] if I4.ndim == 3 else I4, tgt, k, thr)
+    cp, _ = ctx.scanset_download(co); dp, _ = ctx.scanset_download(di)
+    assert 0 < len(edi) < len(q)
+    assert np.array_equal(cp.view(np.uint32), eco.view(np.uint32)) and np.array_equal(dp.view(np.uint32), edi.view(np.uint32))
+    near, far = ctx.knn_split_cloud(ctx.cloud_upload(q), th, k, thr)
+    assert np.array_equal(ctx.cloud_download(near), q[lab == 0]) and np.array_equal(ctx.cloud_download(far), q[lab == 1])
 
 
 def test_argument_errors(ctx):
