@@ -78,7 +78,7 @@ class ClockSampler:
     calling nvmlDeviceGetClockInfo / nvmlDeviceGetCurrentClocksEventReasons; `nvidia-smi -lms` was measured to slow the
     launch-heavy step by ~30 % through driver-lock contention, direct NVML calls do not)."""
 
-    def __init__(self, gpu_index, period_s=0.05):
+    def __init__(self, gpu_index, period_s=0.25):
         self.gpu, self.period, self.rows, self.stop_flag, self.thread, self.err = gpu_index, period_s, [], False, None, None
 
     def start(self):
@@ -137,6 +137,7 @@ def owned_blocks(rank, world, kf, split):
 
 def gen_blocks(rank, world, kf, split):
     import synth
+    from lt_mapper_b200 import removert
     threads = max(1, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))))
     out = {}
     for s, (k0, n) in owned_blocks(rank, world, kf, split).items():
@@ -144,7 +145,7 @@ def gen_blocks(rank, world, kf, split):
             out[s] = None
             continue
         d = synth.make_session(s, n, k0=k0, threads=threads)
-        out[s] = (d, np.stack([np.linalg.inv(p) for p in d.poses]))   # the C-ABI takes inverse poses as an input (ltr_b200.h)
+        out[s] = (d, removert.inverse_poses(d.poses))   # the C-ABI takes inverse poses as an input (ltr_b200.h)
     return out
 
 
@@ -422,11 +423,16 @@ def main():
     stage_t = {}
     barrier()
     R.ctx.timer_start()
+    diag = os.environ.get("LTR_BENCH_DIAG") == "1"
     for _ in range(args.steps):
         l2_flush()                    # L2 flush between timed iterations
+        if diag:
+            R.ctx.synchronize(); t_r0 = time.perf_counter()
         R.reset_to_step0()
+        if diag:
+            R.ctx.synchronize(); stage_t["reset(diag)"] = stage_t.get("reset(diag)", 0.0) + time.perf_counter() - t_r0
         R.run_step12()
-        for k in ("hd_remove", "hd_knn", "exchange", "parse_static", "ld_knn", "ld_filter", "ld_merge_viz"):
+        for k in ("hd_remove", "hd_knn", "exchange", "parse_static", "ld_knn", "ld_filter", "ld_merge_viz", "step12"):
             stage_t[k] = stage_t.get(k, 0.0) + R.timing(k)
     ms_total = R.ctx.timer_stop()
     barrier()

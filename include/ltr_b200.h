@@ -81,6 +81,10 @@ int64_t ltr_voxel_shortcuts(const ltr_ctx* ctx);
 int ltr_memory_stats(const ltr_ctx* ctx, int64_t* stats3);
 
 /* ---- data movement -------------------------------------------------------------------------- */
+/* Page-locked host staging memory for the uploads / downloads below (cudaMallocHost): copies from pageable memory run at a fraction
+ * of the link rate and block the caller. */
+int ltr_pinned_alloc(size_t bytes, void** out);
+void ltr_pinned_free(void* p);
 int ltr_cloud_upload(ltr_ctx* ctx, const float* xyzi, int64_t n, ltr_cloud* out);
 int ltr_cloud_size(ltr_ctx* ctx, ltr_cloud c, int64_t* n);
 int ltr_cloud_download(ltr_ctx* ctx, ltr_cloud c, float* xyzi, int64_t capacity, int64_t* n);

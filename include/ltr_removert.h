@@ -74,6 +74,11 @@ ltr_ctx* ltrh_context(ltrh_removerter* r);
 int ltrh_comm_init_nccl(ltrh_removerter* r, const uint8_t* id128, int32_t rank, int32_t world, int32_t split_sessions);
 int ltrh_owns_session(ltrh_removerter* r, int32_t sess);   /* 1 iff this rank holds keyframes of `sess` */
 
+/* Inverse keyframe poses the way the reference obtains them (Session.cpp:110, Eigen::Matrix4d::inverse(): general 4x4 inverse by cofactors).
+ * ltrh_load_session takes inverse poses as an INPUT so that every implementation works from identical doubles; callers that do not have the
+ * reference's inverses at hand should use this one rather than an LU-based inverse, whose last bits differ. */
+void ltrh_invert_poses(const double* poses16, int32_t K, double* out16);
+
 /* sess: 0 = central, 1 = query.  Keyframes are this rank's block (all keyframes when world == 1). */
 int ltrh_load_session(ltrh_removerter* r, int32_t sess, const float* xyzi, const int64_t* offsets, const double* poses,
                       const double* inv_poses, int32_t K);

@@ -37,7 +37,7 @@ EXPORTS = [
     "ltr_preclean", "ltr_merge_scans_global", "ltr_voxel_centroid", "ltr_voxel_centroid_per_keyframe", "ltr_remove_pass",
     "ltr_flags_device_ptr", "ltr_flags_download", "ltr_flags_upload", "ltr_apply_partition", "ltr_parse_projected",
     "ltr_knn_diff", "ltr_knn_split_cloud", "ltr_debug_pixel_index", "ltr_debug_scan_rimg", "ltr_debug_fast_project", "ltr_debug_atan_sweep", "ltr_debug_margins", "ltr_reset_rimg_size", "ltr_last_pass_stats", "ltr_profile_get", "ltr_profile_reset", "ltr_timer_start", "ltr_timer_stop", "ltr_trace_dump",
-    "ltr_nccl_unique_id", "ltr_nccl_init", "ltr_nccl_split", "ltr_nccl_info", "ltr_nccl_destroy", "ltr_nccl_version", "ltr_nccl_allreduce_flags",
+    "ltr_pinned_alloc", "ltr_pinned_free", "ltr_nccl_unique_id", "ltr_nccl_init", "ltr_nccl_split", "ltr_nccl_info", "ltr_nccl_destroy", "ltr_nccl_version", "ltr_nccl_allreduce_flags",
     "ltr_nccl_allgather_clouds", "ltr_nccl_exchange_clouds", "ltr_nccl_allgather_i64", "ltr_nccl_max_f64", "ltr_nccl_barrier", "ltr_stream_handle",
 ]
 
@@ -107,6 +107,9 @@ def lib():
     L.ltr_timer_start.argtypes = [vp]
     L.ltr_trace_dump.argtypes = [vp, i32]
     L.ltr_timer_stop.argtypes = [vp, P(ctypes.c_double)]
+    L.ltr_pinned_alloc.argtypes = [ctypes.c_size_t, P(vp)]
+    L.ltr_pinned_free.argtypes = [vp]
+    L.ltr_pinned_free.restype = None
     L.ltr_nccl_unique_id.argtypes = [vp]
     L.ltr_nccl_init.argtypes = [vp, vp, i32, i32, P(i32)]
     L.ltr_nccl_split.argtypes = [vp, i32, i32, i32, P(i32)]

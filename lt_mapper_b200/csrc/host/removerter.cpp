@@ -49,7 +49,11 @@ Removerter::Removerter(const ltrh_params& p) : P(p) {
     comm.rank = 0; comm.world = 1;
 }
 
-Removerter::~Removerter() { if (ctx) ltr_destroy(ctx); }
+Removerter::~Removerter() {
+    ltr_pinned_free(pin_in_);
+    ltr_pinned_free(pin_out_);
+    if (ctx) ltr_destroy(ctx);
+}
 
 int Removerter::fail(int code, const std::string& msg) { err = msg; return code; }
 
@@ -76,6 +80,8 @@ static void invert4x4(const double* m, double* out) {
     const double idet = 1.0 / det;
     for (int i = 0; i < 16; ++i) out[i] = inv[i] * idet;
 }
+
+void invert4x4_public(const double* m, double* out) { invert4x4(m, out); }
 
 int Removerter::init() {
     ltr_config cfg;
@@ -650,9 +656,19 @@ int Removerter::cascade_promote_updated() {
     if (owns(C) && C.keyframe_scans_updated_ < 0) return fail(LTR_ERR_INVALID, "cascade: Step 3 has not run (no keyframe_scans_updated_)");
     int32_t K = 0; int64_t total = 0;
     if (owns(C)) CK(ltr_scanset_info(ctx, C.keyframe_scans_updated_, &K, &total));
-    std::vector<float> xyzi((size_t)std::max<int64_t>(total, 1) * 4);
+    // page-locked staging in both directions (a pageable 1 GB round trip costs more than Steps 0-3 of a session)
+    // (kept across promotions: page-locking a gigabyte is itself slow)
+    auto grow = [&](void** p, size_t* cap, size_t bytes) {
+        if (*cap >= bytes) return true;
+        ltr_pinned_free(*p); *p = nullptr; *cap = 0;
+        if (ltr_pinned_alloc(bytes + bytes / 4, p) != LTR_OK) return false;
+        *cap = bytes + bytes / 4;
+        return true;
+    };
+    if (!grow(&pin_in_, &pin_in_cap_, (size_t)std::max<int64_t>(total, 1) * 16)) return fail(LTR_ERR_NOMEM, "cascade: pinned staging allocation failed");
+    float* xyzi = (float*)pin_in_;
     std::vector<int64_t> off((size_t)K + 1, 0);
-    if (owns(C)) CK(ltr_scanset_download(ctx, C.keyframe_scans_updated_, xyzi.data(), total, off.data()));
+    if (owns(C)) CK(ltr_scanset_download(ctx, C.keyframe_scans_updated_, xyzi, total, off.data()));
     // host-side load-time VoxelGrid, keyframes are independent (the reference's loadKeyframes loop is serial; the per-scan
     // arithmetic and its std::sort are unchanged, only different scans run on different threads)
     std::vector<HostCloud> grids((size_t)K);
@@ -665,12 +681,14 @@ int Removerter::cascade_promote_updated() {
         }
         grids[(size_t)k] = voxel_grid(in, P.downsample_voxel_size, nullptr);
     }
-    std::vector<float> out;
     std::vector<int64_t> out_off((size_t)K + 1, 0);
-    out.reserve(xyzi.size());
+    for (int k = 0; k < K; ++k) out_off[(size_t)k + 1] = out_off[(size_t)k] + (int64_t)grids[(size_t)k].size();
+    if (!grow(&pin_out_, &pin_out_cap_, (size_t)std::max<int64_t>(out_off[(size_t)K], 1) * 16)) return fail(LTR_ERR_NOMEM, "cascade: pinned staging allocation failed");
+    float* out = (float*)pin_out_;
+#pragma omp parallel for schedule(dynamic, 1)
     for (int k = 0; k < K; ++k) {
-        for (const auto& p : grids[(size_t)k]) { out.push_back(p.x); out.push_back(p.y); out.push_back(p.z); out.push_back(p.intensity); }
-        out_off[(size_t)k + 1] = (int64_t)(out.size() / 4);
+        float* o = out + (size_t)out_off[(size_t)k] * 4;
+        for (const auto& p : grids[(size_t)k]) { *o++ = p.x; *o++ = p.y; *o++ = p.z; *o++ = p.intensity; }
     }
     for (Session* s : {&central_sess_, &query_sess_}) {
         for (auto& kv : s->cloud_names()) if (*kv.second >= 0) { CK(ltr_cloud_free(ctx, *kv.second)); *kv.second = -1; }
@@ -682,8 +700,7 @@ int Removerter::cascade_promote_updated() {
     query_sess_.num_keyframes_ = 0;
     if (owns(C)) {
         ltr_scanset ss;
-        if (out.empty()) out.resize(4);
-        CK(ltr_scanset_upload(ctx, out.data(), out_off.data(), K, &ss));
+        CK(ltr_scanset_upload(ctx, out, out_off.data(), K, &ss));
         C.keyframe_scans_ = ss;
     }
     log.clear();
@@ -746,6 +763,10 @@ int ltrh_comm_init_nccl(ltrh_removerter* r, const uint8_t* id128, int32_t rank, 
     if (!r || !id128) return LTR_ERR_INVALID;
     r->R->err.clear();
     return r->R->comm_init_nccl(id128, rank, world, split_sessions);
+}
+// Eigen::Matrix4d::inverse() stand-in (general 4x4 inverse by cofactors) for the inverse keyframe poses of Session.cpp:110
+void ltrh_invert_poses(const double* poses16, int32_t K, double* out16) {
+    for (int k = 0; k < K; ++k) ltremovert_b200::invert4x4_public(poses16 + 16 * (size_t)k, out16 + 16 * (size_t)k);
 }
 int ltrh_owns_session(ltrh_removerter* r, int32_t sess) { return r && r->R->owns(sess == 0 ? r->R->central_sess_ : r->R->query_sess_) ? 1 : 0; }
 

@@ -12,6 +12,8 @@
 
 namespace ltremovert_b200 {
 
+void invert4x4_public(const double* m, double* out);   // general 4x4 inverse by cofactors (removerter.cpp)
+
 struct PassLog { std::string what; int64_t n_map, n_dynamic, n_static_after, n_dynamic_after; };
 
 class Removerter;
@@ -106,6 +108,8 @@ public:
     int nccl_world = -1;      // ltr_nccl communicator handles: everyone, ...
     int nccl_group[2] = {-1, -1};   // ... and the ranks that own session s
     int group_world = 1;
+    void *pin_in_ = nullptr, *pin_out_ = nullptr;     // page-locked staging of cascade_promote_updated, grown on demand
+    size_t pin_in_cap_ = 0, pin_out_cap_ = 0;
     Session central_sess_, query_sess_;
     std::map<std::string, ltr_cloud> saved;
     std::map<std::string, double> timing;

@@ -70,7 +70,7 @@ void dev_free(ltr_ctx* ctx, void* p) {
     ctx->live_bytes -= sz;
     ctx->free_blocks.emplace(sz, p);
     ctx->cached_bytes += sz;
-    if (ctx->cached_bytes > ((size_t)48 << 30)) {   // bound the cache: drop everything that is not in use
+    if (ctx->cached_bytes > ctx->cache_limit_bytes) {   // bound the cache: drop everything that is not in use
         ctx->n_purges++;
         cudaStreamSynchronize(ctx->stream);
         for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
@@ -269,6 +269,7 @@ int ltr_create(ltr_ctx** out, const ltr_config* cfg) {
     if (ctx->cfg.keyframe_batch <= 0) ctx->cfg.keyframe_batch = 32;
     ctx->device = cfg->device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->cache_limit_bytes = (size_t)((double)prop.totalGlobalMem * 0.45);   // idle blocks kept for reuse: at most 45 % of the device memory
     ctx->ext_identity = is_identity(cfg->lidar2base) && is_identity(cfg->base2lidar);
     { const char* t = getenv("LTR_TRACE"); ctx->trace = t && t[0] == '1'; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -324,6 +325,15 @@ int ltr_synchronize(ltr_ctx* ctx) {
     LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return LTR_OK;
 }
+
+// page-locked host staging memory (full-rate, truly asynchronous H2D / D2H); not tied to a context
+int ltr_pinned_alloc(size_t bytes, void** out) {
+    if (!out) return LTR_ERR_INVALID;
+    *out = nullptr;
+    if (bytes == 0) return LTR_OK;
+    return cudaMallocHost(out, bytes) == cudaSuccess ? LTR_OK : LTR_ERR_NOMEM;
+}
+void ltr_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 int64_t ltr_kernel_launches(const ltr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* ltr_stream_handle(ltr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

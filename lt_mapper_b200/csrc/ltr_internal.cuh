@@ -65,6 +65,7 @@ struct ltr_ctx {
     std::vector<ltr::DevPoses> poses;
     std::vector<ltr::NcclComm> nccl;           // communicators created by ltr_nccl_init / ltr_nccl_split
     int64_t launches = 0;
+    bool rs_attr_set = false;    // radix-sort scatter kernel opted in to > 48 KB shared memory on this device
     int64_t vox_shortcuts = 0;   // voxelisations answered by the already-one-point-per-voxel shortcut (util.cu)
     bool ext_identity = true;     // base2lidar/lidar2base exactly identity -> second transform step is exact and skipped
     double* d_ext = nullptr;      // 24 doubles: base2lidar rows 0..2, lidar2base rows 0..2
@@ -79,6 +80,7 @@ struct ltr_ctx {
     std::multimap<size_t, void*> free_blocks;  // size -> block
     std::map<void*, size_t> live_blocks;       // block -> size
     size_t cached_bytes = 0, live_bytes = 0, peak_live_bytes = 0;
+    size_t cache_limit_bytes = (size_t)48 << 30;
     long n_cuda_malloc = 0, n_cache_hits = 0, n_purges = 0;
     bool trace = false;                        // LTR_TRACE=1: per-entry-point synchronised host timings, dumped at ltr_destroy
     std::map<std::string, std::pair<double, long>> trace_acc; // [0] remove-pass map kernel us, [1] launches, [2] algorithmic bytes, [3] point-projections

@@ -313,6 +313,10 @@ static inline unsigned fast_grid(const ltr_ctx* ctx, int64_t n) {
 
 static inline size_t fast_smem_bytes() { return (size_t)(kFastThreads / 32) * 2 * kQueueCap * sizeof(uint64_t); }
 
+static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, max_blocks));
+}
+
 static inline KfBatch make_kf_batch(const DevPoses& poses, int k0, int nb) {
     KfBatch kb;
     std::memset(&kb, 0, sizeof(kb));
@@ -321,22 +325,44 @@ static inline KfBatch make_kf_batch(const DevPoses& poses, int k0, int nb) {
 }
 
 // one launch of the fast projection over the keyframes [k0, k0 + nb) of `poses`
-template <bool kCand>
+template <bool kCand, bool kDeferred = false>
 static void launch_fast(ltr_ctx* ctx, const DevCloud& map, const DevPoses& poses, int k0, int nb, const ImgShape& g, const FastCfg& fc,
-                        const uint32_t* rimg, const uint32_t* test_img, float thres, uint64_t* win, uint32_t* amin, const CullArgs& ca) {
+                        const uint32_t* rimg, const uint32_t* test_img, float thres, uint64_t* win, uint32_t* amin, const CullArgs& ca,
+                        DeferredArgs da = DeferredArgs{nullptr, nullptr, nullptr, nullptr, 0}) {
     const unsigned fb = fast_grid(ctx, map.n);
     unsigned int* work = (unsigned int*)(ctx->d_counters + 4);
     cudaMemsetAsync(work, 0, sizeof(unsigned int), ctx->stream);
     const KfBatch kb = make_kf_batch(poses, k0, nb);
-    if (fc.el_direct) map_project_fast_kernel<kCand, true><<<fb, kFastThreads, fast_smem_bytes(), ctx->stream>>>(view(map), kb, poses.d, k0, nb, ctx->d_ext,
-        ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, test_img, thres, win, amin, ca, ctx->d_counters, work);
-    else map_project_fast_kernel<kCand, false><<<fb, kFastThreads, fast_smem_bytes(), ctx->stream>>>(view(map), kb, poses.d, k0, nb, ctx->d_ext,
-        ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, test_img, thres, win, amin, ca, ctx->d_counters, work);
+    if (kDeferred) {
+        cudaMemsetAsync(da.best, 0xff, (size_t)nb * g.rows * g.cols * sizeof(unsigned long long), ctx->stream);   // "no pair yet"
+        cudaMemsetAsync(da.count, 0, sizeof(unsigned int), ctx->stream);
+    }
+    if (fc.el_direct) map_project_fast_kernel<kCand, true, kDeferred><<<fb, kFastThreads, fast_smem_bytes(), ctx->stream>>>(view(map), kb, poses.d, k0, nb, ctx->d_ext,
+        ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, test_img, thres, win, amin, ca, ctx->d_counters, work, da);
+    else map_project_fast_kernel<kCand, false, kDeferred><<<fb, kFastThreads, fast_smem_bytes(), ctx->stream>>>(view(map), kb, poses.d, k0, nb, ctx->d_ext,
+        ctx->ext_identity ? 1 : 0, ctx->cfg.transform_order, g, fc, rimg, test_img, thres, win, amin, ca, ctx->d_counters, work, da);
+    if (kDeferred) {
+        const int64_t total = (int64_t)nb * g.rows * g.cols;
+        ctx->launches++;
+        deferred_resolve_kernel<<<grid_for(total, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(view(map), poses.d, k0, nb, ctx->d_ext, ctx->ext_identity ? 1 : 0,
+            ctx->cfg.transform_order, (uint32_t)(g.rows * g.cols), da, win);
+    }
 }
 
-static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
-    return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, max_blocks));
+// scratch of the deferred true-minimum mode for launches of up to B keyframes: best image + overflow list + its counter
+constexpr unsigned kDeferredListCap = 8u << 20;   // entries (64 MB); a typical launch appends a few 10^4
+static int deferred_alloc(ltr_ctx* ctx, int B, int64_t npx, void** block, DeferredArgs* da) {
+    const size_t best_bytes = (size_t)B * npx * sizeof(unsigned long long);
+    LTR_TRY(dev_alloc(ctx, block, best_bytes + (size_t)kDeferredListCap * sizeof(unsigned long long) + 256));
+    da->best = (unsigned long long*)*block;
+    da->list = da->best + (size_t)B * npx;
+    da->count = (unsigned int*)(da->list + kDeferredListCap);
+    da->overflow = da->count + 1;
+    da->capacity = kDeferredListCap;
+    LTR_CUDA(ctx, cudaMemsetAsync(da->count, 0, 2 * sizeof(unsigned int), ctx->stream));
+    return LTR_OK;
 }
+
 
 }  // namespace ltr
 
@@ -344,10 +370,24 @@ using namespace ltr;
 
 extern "C" {
 
+static int remove_pass_impl(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_poses poses_h, int32_t kf_begin, int32_t kf_end,
+                            int32_t mode, float res_alpha, float diff_thres, int32_t accumulate, int64_t* n_dynamic, bool allow_deferred, bool* overflowed);
+
 int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_poses poses_h, int32_t kf_begin, int32_t kf_end,
                     int32_t mode, float res_alpha, float diff_thres, int32_t accumulate, int64_t* n_dynamic) {
     ApiTrace tr__(ctx, "ltr_remove_pass");
     if (!ctx) return LTR_ERR_INVALID;
+    bool overflowed = false;
+    // ND (true per-pixel minimum) runs in the deferred mode of project_fast.cuh unless the flags accumulate into earlier ones (a run whose
+    // overflow list filled up would have to be undone); a full list -- never seen, the list holds 8 M entries -- repeats the pass in the immediate mode
+    LTR_TRY(remove_pass_impl(ctx, map_h, scans_h, poses_h, kf_begin, kf_end, mode, res_alpha, diff_thres, accumulate, n_dynamic, !accumulate, &overflowed));
+    if (overflowed) LTR_TRY(remove_pass_impl(ctx, map_h, scans_h, poses_h, kf_begin, kf_end, mode, res_alpha, diff_thres, accumulate, n_dynamic, false, &overflowed));
+    return LTR_OK;
+}
+
+static int remove_pass_impl(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_poses poses_h, int32_t kf_begin, int32_t kf_end,
+                            int32_t mode, float res_alpha, float diff_thres, int32_t accumulate, int64_t* n_dynamic, bool allow_deferred, bool* overflowed) {
+    *overflowed = false;
     DevCloud* map;
     DevScanSet* scans;
     DevPoses* poses;
@@ -373,6 +413,11 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     if (use_fast && cand && map->n > 0 && kf_end > kf_begin) LTR_TRY(empty_scan_shortcut_ok(ctx, *map, *poses, kf_begin, kf_end, &shortcut));
     const FastCfg fc = make_fast_cfg(rows, cols, ctx->cfg.vfov_deg, ctx->cfg.hfov_deg, shortcut);
     if (use_fast) LTR_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    const bool use_deferred = use_fast && !cand && allow_deferred;
+    void* p_def = nullptr;
+    ScratchGuard g_def(ctx, &p_def);
+    DeferredArgs da{nullptr, nullptr, nullptr, nullptr, 0};
+    if (use_deferred && map->n > 0 && kf_end > kf_begin) LTR_TRY(deferred_alloc(ctx, B, npx, &p_def, &da));
     // tile culling (project_cull.cuh): scan-minus-map variants only, one keyframe per lane -> launches of at most 32 keyframes
     CullArgs ca;
     std::memset(&ca, 0, sizeof(ca));
@@ -441,6 +486,7 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
             launch_units.push_back(nb);
             if (use_fast) {
                 if (cand) launch_fast<true>(ctx, *map, *poses, k0, nb, g, fc, rimg, test_img, diff_thres, win, amin, ca);
+                else if (use_deferred) launch_fast<false, true>(ctx, *map, *poses, k0, nb, g, fc, rimg, amin, diff_thres, win, amin, ca, da);
                 else launch_fast<false>(ctx, *map, *poses, k0, nb, g, fc, rimg, amin, diff_thres, win, amin, ca);
             } else {
                 const unsigned mb = (unsigned)((map->n + 255) / 256);
@@ -462,7 +508,11 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     g_pyr.release();
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     if (n_dynamic) LTR_TRY(count_flags(ctx, map->flags, map->n, n_dynamic));
+    unsigned int h_over = 0;
+    if (da.overflow) LTR_CUDA(ctx, cudaMemcpyAsync(&h_over, da.overflow, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     LTR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    if (da.overflow) { LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); *overflowed = h_over != 0; }
+    g_def.release();
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     prof_collect(ctx, 0, 12.0 * (double)map->n + (double)map->n / 8.0, (double)map->n, launch_units);
@@ -473,9 +523,24 @@ int ltr_remove_pass(ltr_ctx* ctx, ltr_cloud map_h, ltr_scanset scans_h, ltr_pose
     return LTR_OK;
 }
 
+static int parse_projected_impl(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_t kf_begin, int32_t kf_end, float res_alpha, ltr_scanset* out,
+                                bool allow_deferred, bool* overflowed);
+
 int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_t kf_begin, int32_t kf_end, float res_alpha, ltr_scanset* out) {
     ApiTrace tr__(ctx, "ltr_parse_projected");
     if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    bool overflowed = false;
+    LTR_TRY(parse_projected_impl(ctx, map_h, poses_h, kf_begin, kf_end, res_alpha, out, true, &overflowed));
+    if (overflowed) {   // the deferred mode's candidate list filled up (8 M entries; never seen): repeat with the immediate mode
+        LTR_TRY(ltr_scanset_free(ctx, *out));
+        LTR_TRY(parse_projected_impl(ctx, map_h, poses_h, kf_begin, kf_end, res_alpha, out, false, &overflowed));
+    }
+    return LTR_OK;
+}
+
+static int parse_projected_impl(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_t kf_begin, int32_t kf_end, float res_alpha, ltr_scanset* out,
+                                bool allow_deferred, bool* overflowed) {
+    *overflowed = false;
     DevCloud* map;
     DevPoses* poses;
     LTR_TRY(cloud_get(ctx, map_h, &map));
@@ -495,12 +560,15 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
     const bool use_fast = ctx->cfg.fast_path && npx <= (1 << 18);
     if (use_fast) LTR_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    void *p_list = nullptr, *p_cnt = nullptr;
-    ScratchGuard g_list(ctx, &p_list), g_cnt(ctx, &p_cnt);
+    void *p_list = nullptr, *p_cnt = nullptr, *p_def = nullptr;
+    ScratchGuard g_list(ctx, &p_list), g_cnt(ctx, &p_cnt), g_def(ctx, &p_def);
+    DeferredArgs da{nullptr, nullptr, nullptr, nullptr, 0};
+    const bool use_deferred = use_fast && allow_deferred;
     std::vector<int> launch_units;
     ctx->ev_used = 0;
     if (K > 0 && mapc.n > 0) {
         const int B = std::max(1, std::min(std::min(ctx->cfg.keyframe_batch, use_fast ? kFastMaxBatch : 400), K));
+        if (use_deferred) LTR_TRY(deferred_alloc(ctx, B, npx, &p_def, &da));
         void *p_win = nullptr, *p_amin = nullptr;
         ScratchGuard g_win(ctx, &p_win), g_amin(ctx, &p_amin);
         LTR_TRY(dev_alloc(ctx, &p_win, (size_t)B * npx * sizeof(uint64_t)));
@@ -522,7 +590,8 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
                 LTR_LAUNCH_CHECK(ctx);
                 CullArgs no_cull;
                 std::memset(&no_cull, 0, sizeof(no_cull));
-                launch_fast<false>(ctx, mapc, posc, kf_begin + k0, nb, g, fc, nullptr, amin, 0.0f, win, amin, no_cull);
+                if (use_deferred) launch_fast<false, true>(ctx, mapc, posc, kf_begin + k0, nb, g, fc, nullptr, amin, 0.0f, win, amin, no_cull, da);
+                else launch_fast<false>(ctx, mapc, posc, kf_begin + k0, nb, g, fc, nullptr, amin, 0.0f, win, amin, no_cull);
             } else {
                 const unsigned mb = (unsigned)((mapc.n + 255) / 256);
                 map_project_kernel<false><<<mb, 256, (size_t)nb * 12 * sizeof(double), ctx->stream>>>(view(mapc), posc.d, kf_begin + k0, nb, ctx->d_ext,
@@ -539,8 +608,12 @@ int ltr_parse_projected(ltr_ctx* ctx, ltr_cloud map_h, ltr_poses poses_h, int32_
         g_win.release();
         g_amin.release();
         std::vector<unsigned int> cnt((size_t)K);
+        unsigned int h_over = 0;
         LTR_CUDA(ctx, cudaMemcpyAsync(cnt.data(), p_cnt, (size_t)K * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (da.overflow) LTR_CUDA(ctx, cudaMemcpyAsync(&h_over, da.overflow, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        g_def.release();
+        if (h_over) *overflowed = true;
         for (int k = 0; k < K; ++k) off[k + 1] = off[k] + cnt[k];
     }
     LTR_TRY(scanset_new(ctx, off, out));

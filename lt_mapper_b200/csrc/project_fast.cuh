@@ -253,14 +253,32 @@ struct KfBatch { float kf[kFastMaxBatch][16]; };
 // Hot loop (profiles/r02_sass_map_project_fast.md): the kernel is issue-bound, so the common "no effect" path is one straight line
 // per point -- transform (12), azimuth (16), ranges (7), elevation (10), pixel + certainty (14), one gather + compare (5) -- and
 // rare pairs reserve a queue slot with a shared-memory atomic (no ballots on the common path).
-template <bool kCandidatesOnly, bool kElDirect>
+// Deferred true-minimum mode (kDeferred; ND pass and visible-point extraction).  The pixel winner is the point of minimum EXACT
+// range (lowest index on ties); an approximate range is within `band/2 = m_r_abs + m_r_rel r` of the exact one.  Instead of sending
+// every running minimum through the exact arithmetic (on Morton-ordered surface patches that was 44 % of all pairs), the scan only
+// maintains, per pixel, the pair of smallest APPROXIMATE range (`best`, 64-bit atomicMin of range bits | index) and appends to a
+// small overflow list every pair that is within `band` of the best known at its time without becoming the best, as well as a
+// displaced best that is within `band` of its successor.  `best` only decreases, so every point whose approximate range is within
+// `band` of the FINAL best -- a superset of the points that can be the exact winner -- is either the final best or on the list.
+// deferred_resolve_kernel then evaluates exactly the final best of every pixel and the list entries (a few per cent of a pixel
+// count instead of tens of per cent of all pairs).  A full list sets `overflow_count` beyond the capacity; the host then repeats the
+// call with the immediate mode.
+struct DeferredArgs {
+    unsigned long long* best;      // [keyframes in launch][npx], initialised to ~0
+    unsigned long long* list;      // overflow entries: q_pack(index, pixel, keyframe)
+    unsigned int* count;           // entries appended by the current launch (may exceed capacity)
+    unsigned int* overflow;        // set to 1 when that happened (sticky over the launches of a call)
+    unsigned int capacity;
+};
+
+template <bool kCandidatesOnly, bool kElDirect, bool kDeferred = false>
 __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) map_project_fast_kernel(PtrView map, const __grid_constant__ KfBatch kb, const double* __restrict__ poses,
                                                                         int kf0, int nb, const double* __restrict__ ext, int ext_identity, int order,
                                                                         ImgShape g, const __grid_constant__ FastCfg fc, const uint32_t* __restrict__ scan_rimg,
                                                                         const uint32_t* __restrict__ test_img, float thres,
                                                                         uint64_t* __restrict__ win, uint32_t* __restrict__ approx_min,
                                                                         CullArgs ca, unsigned long long* __restrict__ counters,
-                                                                        unsigned int* __restrict__ work_counter) {
+                                                                        unsigned int* __restrict__ work_counter, DeferredArgs da) {
     extern __shared__ uint64_t s_queues[];
     const int warp = threadIdx.x >> 5;
     uint64_t* s_qa = s_queues + warp * (2 * kQueueCap);
@@ -306,6 +324,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) map_project_fast
         const bool kf_ok = kf[15] != 0.0f;
         const uint32_t* __restrict__ test_k = test_img + (size_t)k * npx;    // this keyframe's images
         uint32_t* __restrict__ amin_k = approx_min + (size_t)k * npx;
+        unsigned long long* __restrict__ best_k = kDeferred ? da.best + (size_t)k * npx : nullptr;
         // Phase 1, branch-free: project the thread's points and ISSUE all their image gathers, so that the (mostly L2) latencies of
         // the four loads overlap instead of being paid one after the other behind a branch each.
         float fr_[kFastPts], tv_[kFastPts];
@@ -325,9 +344,49 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) map_project_fast
             certain_[j] = kf_ok & (__fmaf_rn(fc.m_col_b, f.rho_inv_r, dc) < fc.lim_c) & (dr < fc.lim_r);
             pxl_[j] = (uint32_t)(r * g.cols + c);
             fr_[j] = f.r;
-            tv_[j] = __uint_as_float(test_k[pxl_[j]]);      // unconditional: the index is always inside the image
+            // unconditional: the index is always inside the image (deferred mode: the range word of the pixel's best pair)
+            tv_[j] = kDeferred ? __uint_as_float(reinterpret_cast<const uint32_t*>(best_k)[2 * pxl_[j] + 1]) : __uint_as_float(test_k[pxl_[j]]);
         }
         // Phase 2: decide.  Almost every pair ends at the first comparison.
+        if (kDeferred) {
+            // 2a: issue the atomics of all four points back to back (their round trips overlap), 2b: use what they returned
+            unsigned long long old_[kFastPts];
+            bool enter_[kFastPts], tried_[kFastPts];
+#pragma unroll
+            for (int j = 0; j < kFastPts; ++j) {
+                const float fr = fr_[j], tv = tv_[j];
+                // tv = approximate range of the pixel's best pair as read in phase 1 (all-ones bits = NaN while the pixel is empty;
+                // every comparison is written so that NaN means "consider the pair")
+                enter_[j] = certain_[j] && !(fr > __fadd_rn(tv, __fmaf_rn(fc.mr2_rel, fr, fc.mr2_abs)));
+                tried_[j] = enter_[j] && !(fr >= tv);            // looks like a new best
+                old_[j] = 0ull;
+                if (tried_[j]) {
+                    const uint32_t mi = (uint32_t)(base + j * 32 < map.n ? base + j * 32 : map.n - 1);
+                    old_[j] = atomicMin(&best_k[pxl_[j]], ((unsigned long long)__float_as_uint(fr) << 32) | mi);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kFastPts; ++j) {
+                if (enter_[j]) {
+                    const float fr = fr_[j];
+                    const uint32_t mi = (uint32_t)(base + j * 32 < map.n ? base + j * 32 : map.n - 1);
+                    const unsigned long long v = ((unsigned long long)__float_as_uint(fr) << 32) | mi;
+                    unsigned long long loser = v;          // fr >= tv: the pair read in phase 1 (or a nearer one) stays the best, v is a candidate
+                    float r_win = tv_[j];
+                    if (tried_[j]) {
+                        if (v < old_[j]) { loser = old_[j]; r_win = fr; }                        // v is the best now; the displaced pair may still matter
+                        else r_win = __uint_as_float((uint32_t)(old_[j] >> 32));                 // somebody nearer got there first
+                    }
+                    const float r_los = __uint_as_float((uint32_t)(loser >> 32));
+                    if (loser != ~0ull && !(r_los > __fadd_rn(r_win, __fmaf_rn(fc.mr2_rel, r_los, fc.mr2_abs)))) {
+                        const unsigned slot = atomicAdd(da.count, 1u);
+                        if (slot < da.capacity) da.list[slot] = q_pack((uint32_t)loser, pxl_[j], (uint32_t)k);
+                    }
+                } else if (!certain_[j]) {
+                    s_qb[atomicAdd(&s_cnt[warp][1], 1)] = q_pack((uint32_t)(base + j * 32 < map.n ? base + j * 32 : map.n - 1), 0u, (uint32_t)k);
+                }
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < kFastPts; ++j) {
             const float fr = fr_[j], tv = tv_[j];
@@ -348,6 +407,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) map_project_fast
             } else {
                 s_qb[atomicAdd(&s_cnt[warp][1], 1)] = q_pack((uint32_t)(base + j * 32 < map.n ? base + j * 32 : map.n - 1), 0u, (uint32_t)k);
             }
+        }
         }
         __syncwarp();
         int qa = *(volatile int*)&s_cnt[warp][0];
@@ -387,6 +447,25 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) map_project_fast
     if (lane == 0 && counters) {
         atomicAdd(&counters[0], (unsigned long long)n_a); atomicAdd(&counters[1], (unsigned long long)n_atomics); atomicAdd(&counters[2], (unsigned long long)n_b);
         if (n_culled) atomicAdd(&counters[3], (unsigned long long)n_culled * (32ull * kFastPts));   // pairs skipped by tile culling
+    }
+}
+
+// Deferred true-minimum mode, second half: the exact (range, index) key of the final best pair of every pixel and of every list entry
+// goes into the winner image with the same 64-bit atomicMin as everywhere else.
+__global__ void __launch_bounds__(256) deferred_resolve_kernel(PtrView map, const double* __restrict__ poses, int kf0, int nb, const double* __restrict__ ext,
+                                                               int ext_identity, int order, uint32_t npx, DeferredArgs da, uint64_t* __restrict__ win) {
+    const int64_t total = (int64_t)nb * npx;
+    const unsigned n_list = min(*da.count, da.capacity);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && *da.count > da.capacity) *da.overflow = 1u;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total + n_list; t += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long e;
+        if (t < total) {
+            const unsigned long long b = da.best[t];
+            if (b == ~0ull) continue;
+            e = q_pack((uint32_t)b, (uint32_t)(t % npx), (uint32_t)(t / npx));
+        } else e = da.list[t - total];
+        unsigned n_atomics = 0;
+        exact_range_pair<false>(map, e, poses, kf0, ext, ext_identity, order, npx, nullptr, 0.0f, win, 0, &n_atomics);
     }
 }
 

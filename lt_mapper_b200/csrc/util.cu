@@ -256,12 +256,20 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint64_t* __r
 __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                                                                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                                                                 const uint32_t* __restrict__ offs, int ntiles) {
+    // dynamic shared memory: the tile's keys and values in their sorted-by-digit order, so that the global writes of a digit bucket
+    // are one contiguous, coalesced run instead of 8-byte scatters
+    extern __shared__ uint64_t s_keys[];                            // kRsTile keys, then kRsTile values
+    uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + kRsTile);
     __shared__ uint32_t s_cnt[kRsThreads / 32][256];
-    __shared__ uint32_t s_base[256];
+    __shared__ uint32_t s_excl[256];     // exclusive prefix of the tile's digit counts (position of the bucket inside the tile)
+    __shared__ uint32_t s_gdelta[256];   // global start of the bucket minus its position inside the tile
+    __shared__ uint32_t s_wsum[8];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int t = threadIdx.x; t < (kRsThreads / 32) * 256; t += kRsThreads) (&s_cnt[0][0])[t] = 0;
     __syncthreads();
-    const int64_t chunk = (int64_t)blockIdx.x * kRsTile + (int64_t)warp * (32 * kRsItems);
+    const int64_t tile_base = (int64_t)blockIdx.x * kRsTile;
+    const int64_t chunk = tile_base + (int64_t)warp * (32 * kRsItems);
+    const int tile_n = (int)min((int64_t)kRsTile, n - tile_base);
     uint64_t key[kRsItems];
     uint32_t rank[kRsItems];
     const unsigned lt = (1u << lane) - 1u;
@@ -280,12 +288,20 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t* 
         __syncwarp();
     }
     __syncthreads();
-    {   // exclusive prefix over the warps of the tile, one digit per thread; and the tile's global base per digit
+    {   // per digit (one per thread): exclusive prefix over the warps, tile total; then an exclusive prefix over the digits
         const int d = threadIdx.x;
         uint32_t sum = 0;
 #pragma unroll
         for (int w = 0; w < kRsThreads / 32; ++w) { const uint32_t c = s_cnt[w][d]; s_cnt[w][d] = sum; sum += c; }
-        s_base[d] = offs[(size_t)d * ntiles + blockIdx.x];
+        uint32_t incl = sum;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < (int)warp; ++w) wbase += s_wsum[w];
+        const uint32_t excl = wbase + incl - sum;
+        s_excl[d] = excl;
+        s_gdelta[d] = offs[(size_t)d * ntiles + blockIdx.x] - excl;
     }
     __syncthreads();
 #pragma unroll
@@ -293,18 +309,31 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t* 
         const int64_t i = chunk + r * 32 + lane;
         if (i < n) {
             const unsigned d = (unsigned)(key[r] >> shift) & 255u;
-            const uint32_t pos = s_base[d] + s_cnt[warp][d] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = vals_in[i];
+            const uint32_t lp = s_excl[d] + s_cnt[warp][d] + rank[r];
+            s_keys[lp] = key[r];
+            s_vals[lp] = vals_in[i];
         }
     }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tile_n; t += kRsThreads) {
+        const uint64_t k = s_keys[t];
+        const uint32_t pos = s_gdelta[(unsigned)(k >> shift) & 255u] + (uint32_t)t;
+        keys_out[pos] = k;
+        vals_out[pos] = s_vals[t];
+    }
 }
+
+constexpr size_t kRsScatterSmem = (size_t)kRsTile * (sizeof(uint64_t) + sizeof(uint32_t));   // 48 KB: needs the opt-in above 48 KB - 0
 
 // Sorts (keys0, vals0) using (keys1, vals1) as the other half of the ping-pong; *keys_sorted / *vals_sorted point at the result.
 static int radix_sort_pairs(ltr_ctx* ctx, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, int64_t n, int key_bits,
                             uint64_t** keys_sorted, uint32_t** vals_sorted) {
     *keys_sorted = keys0; *vals_sorted = vals0;
     if (n <= 1 || key_bits <= 0) return LTR_OK;
+    if (!ctx->rs_attr_set) {   // 48 KB dynamic + ~10 KB static shared memory: above the default 48 KB limit (per device)
+        LTR_CUDA(ctx, cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsScatterSmem));
+        ctx->rs_attr_set = true;
+    }
     const int ntiles = (int)((n + kRsTile - 1) / kRsTile);
     void* p = nullptr;
     ScratchGuard g_p(ctx, &p);
@@ -319,7 +348,7 @@ static int radix_sort_pairs(ltr_ctx* ctx, uint64_t* keys0, uint64_t* keys1, uint
             scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(hist, hist, 256 * ntiles);
             LTR_LAUNCH_CHECK(ctx);
         } else LTR_TRY(exclusive_scan_u32(ctx, hist, hist, (int64_t)256 * ntiles));
-        rs_scatter_kernel<<<ntiles, kRsThreads, 0, ctx->stream>>>(kin, kout, vin, vout, n, shift, hist, ntiles);
+        rs_scatter_kernel<<<ntiles, kRsThreads, kRsScatterSmem, ctx->stream>>>(kin, kout, vin, vout, n, shift, hist, ntiles);
         LTR_LAUNCH_CHECK(ctx);
         std::swap(kin, kout); std::swap(vin, vout);
     }

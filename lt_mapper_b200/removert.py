@@ -40,7 +40,7 @@ class Comm(ctypes.Structure):
                 ("allreduce_max_u8", _ALLREDUCE), ("allgather_i64", _ALLGATHER_I64), ("allgatherv_f32", _ALLGATHERV)]
 
 
-HOST_EXPORTS = ["ltrh_params_default", "ltrh_create", "ltrh_destroy", "ltrh_last_error", "ltrh_set_comm", "ltrh_context", "ltrh_comm_init_nccl", "ltrh_owns_session",
+HOST_EXPORTS = ["ltrh_params_default", "ltrh_create", "ltrh_destroy", "ltrh_last_error", "ltrh_set_comm", "ltrh_context", "ltrh_comm_init_nccl", "ltrh_owns_session", "ltrh_invert_poses",
                 "ltrh_load_session", "ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0", "ltrh_cascade_promote_updated", "ltrh_stage", "ltrh_cloud",
                 "ltrh_scanset", "ltrh_timing", "ltrh_log_count", "ltrh_log_get", "ltrh_io_last_error", "ltrh_io_read_pcd", "ltrh_io_write_pcd",
                 "ltrh_io_read_poses", "ltrh_io_parse_keyframes", "ltrh_io_parse_keyframes_in_roi", "ltrh_io_voxel_grid", "ltrh_io_yaml_get"]
@@ -68,6 +68,8 @@ def host_lib():
     L.ltrh_context.restype = vp
     L.ltrh_comm_init_nccl.argtypes = [vp, vp, i32, i32, i32]
     L.ltrh_owns_session.argtypes = [vp, i32]
+    L.ltrh_invert_poses.argtypes = [vp, i32, vp]
+    L.ltrh_invert_poses.restype = None
     L.ltrh_load_session.argtypes = [vp, i32, vp, vp, vp, vp, i32]
     for f in ("ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0", "ltrh_cascade_promote_updated"):
         getattr(L, f).argtypes = [vp]
@@ -188,6 +190,15 @@ class TorchDistComm:
         except Exception as e:  # noqa: BLE001
             print("allgatherv hook failed:", e)
             return 1
+
+
+def inverse_poses(poses):
+    """Inverse keyframe poses as the reference computes them (general 4x4 cofactor inverse, Session.cpp:110); np.linalg.inv differs in the
+    last bits, which is enough to move a few emitted coordinates by one ulp."""
+    p = np.ascontiguousarray(poses, np.float64).reshape(-1, 4, 4)
+    out = np.empty_like(p)
+    host_lib().ltrh_invert_poses(p.ctypes.data, len(p), out.ctypes.data)
+    return out
 
 
 def nccl_unique_id():

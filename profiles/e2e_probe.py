@@ -4,9 +4,10 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from lt_mapper_b200 import removert
-blocks = bench.gen_block(0, 200)
+K = int(sys.argv[1]) if len(sys.argv) > 1 else bench.KF_PER_SESSION
+blocks = bench.gen_block(0, K)
 pinned = [(torch.from_numpy(d.xyzi).pin_memory(), d.offsets, d.poses, inv) for d, inv in blocks]
-R = removert.Removerter(num_knn=1, knn_thr=0.04, schedule=bench.SCHEDULE)
+R = removert.Removerter(num_knn=bench.NUM_KNN, knn_thr=bench.KNN_THR, schedule=bench.schedule())
 def sync(): R.ctx.synchronize()
 for it in range(4):
     t0 = time.perf_counter()

@@ -58,7 +58,7 @@ def main():
                 R.load_session(s, *empty)
                 continue
             d = synth.make_session(s, n, k0=k0, beams=16, az_steps=600, threads=2)
-            R.load_session(s, d.xyzi, d.offsets, d.poses, np.stack([np.linalg.inv(p) for p in d.poses]))
+            R.load_session(s, d.xyzi, d.offsets, d.poses, removert.inverse_poses(d.poses))
 
     load((0, 1))
     R.run_step0(); R.run_step12(); R.run_step3()

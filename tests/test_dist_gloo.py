@@ -79,3 +79,28 @@ def test_two_rank_sharding_and_collectives():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+@pytest.mark.parametrize("world,split", [(1, False), (2, True), (2, False), (4, True), (8, True), (3, False), (8, False)])
+def test_owned_blocks_partition_the_sessions_in_rank_order(world, split):
+    """bench.owned_blocks: per session the blocks of the owning ranks are contiguous, disjoint, in rank order and cover [0, K) --
+    rank-order concatenation must equal keyframe order (utility.cpp:177-189 concatenates in keyframe order)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for K in (1000, 7, 2000):
+        for s in (0, 1):
+            nxt = 0
+            owners = 0
+            for r in range(world):
+                k0, n = bench.owned_blocks(r, world, K, split)[s]
+                if n == 0:
+                    continue
+                owners += 1
+                assert k0 == nxt
+                nxt = k0 + n
+            assert nxt == K
+            assert owners == (world // 2 if split else min(world, K))
+        if split:   # a rank owns keyframes of exactly one session: ranks < world/2 the central one
+            for r in range(world):
+                b = bench.owned_blocks(r, world, K, split)
+                assert (b[0][1] > 0) == (r < world // 2) and (b[1][1] > 0) == (r >= world // 2)

@@ -152,7 +152,7 @@ def test_error_paths_release_their_scratch_memory(ctx):
     hg, hb = ctx.cloud_upload(good), ctx.cloud_upload(bad)
     ss = ctx.scanset_upload(good[:1000], [0, 400, 1000])
     ps = ctx.poses_upload(np.stack([I4, I4]), np.stack([I4, I4]))
-    tiny = ctx.cloud_upload(good[:1])
+    tiny = ctx.cloud_upload(good[:0])                          # an empty kNN target is rejected (PCL asserts on an empty tree)
     base = ctx.memory_stats()[0]
     for _ in range(3):
         with pytest.raises(ltr.LtrError):

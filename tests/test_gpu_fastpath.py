@@ -66,11 +66,13 @@ def test_margins_dominate_measured_deviation(alpha):
             if el_direct:
                 # short elevation path: beyond |qz / rho| = 0.5 the fast elevation is clamped on purpose; there both pre-round rows must
                 # lie at least a full pixel outside the image on the same side (-> the same clamped row), inside it the bound applies
-                t = (local[ok, 2] / np.hypot(local[ok, 0], local[ok, 1]))
-                inside = np.abs(t) < 0.4995
-                beyond = np.abs(t) > 0.5005
-                top = beyond & (t > 0)
-                bot = beyond & (t < 0)
+                # classified by the REFERENCE's own elevation (its pre-round row), not by the generated coordinates: points a fraction of a
+                # millimetre from the sensor move by more than that when the world coordinates are rounded to float
+                ppr_r = rows * 180.0 / (np.pi * 50.0)
+                el_ref = (0.5 * rows - o[:, 5]) / ppr_r
+                inside = np.abs(el_ref) < np.arctan(0.4995)
+                top = el_ref > np.arctan(0.5005)
+                bot = el_ref < -np.arctan(0.5005)
                 assert (o[top, 1] < -1.0).all() and (o[top, 5] < -1.0).all()
                 assert (o[bot, 1] > rows).all() and (o[bot, 5] > rows).all()
                 drow = drow[inside]
