@@ -173,6 +173,11 @@ int ltr_nccl_version(int32_t* v);
 int ltr_nccl_allreduce_flags(ltr_ctx* ctx, int32_t comm, ltr_cloud map);
 /* out[i] = concatenation over ranks 0..world-1 of each rank's local[i]; one size exchange + ONE grouped send/recv for all clouds */
 int ltr_nccl_allgather_clouds(ltr_ctx* ctx, int32_t comm, int32_t count, const ltr_cloud* local, ltr_cloud* out);
+/* octreeDownsampling (utility.cpp:204-219) of the rank-ordered concatenation of every rank's `local` cloud (a cloud merged over all
+ * keyframes, utility.cpp:177-189), WITHOUT gathering the raw points: all-reduced bounding box, key-prefix ranges of equal population,
+ * one exchange of each point to the owner of its range, local voxelisation with the global box, all-gather of the centroid slices.
+ * The result (replicated on every rank) is bit-identical to ltr_voxel_centroid of the gathered cloud. */
+int ltr_nccl_voxel_centroid_merged(ltr_ctx* ctx, int32_t comm, ltr_cloud local, float leaf, ltr_cloud* out);
 /* n_send clouds go to `peer`, n_recv clouds come from `peer` (the peer calls with the mirrored counts) */
 int ltr_nccl_exchange_clouds(ltr_ctx* ctx, int32_t comm, int32_t peer, int32_t n_send, const ltr_cloud* send, int32_t n_recv, ltr_cloud* recv);
 int ltr_nccl_allgather_i64(ltr_ctx* ctx, int32_t comm, const int64_t* local, int32_t count, int64_t* out /* world * count */);

@@ -38,7 +38,7 @@ EXPORTS = [
     "ltr_flags_device_ptr", "ltr_flags_download", "ltr_flags_upload", "ltr_apply_partition", "ltr_parse_projected",
     "ltr_knn_diff", "ltr_knn_split_cloud", "ltr_debug_pixel_index", "ltr_debug_scan_rimg", "ltr_debug_fast_project", "ltr_debug_atan_sweep", "ltr_debug_margins", "ltr_reset_rimg_size", "ltr_last_pass_stats", "ltr_profile_get", "ltr_profile_reset", "ltr_timer_start", "ltr_timer_stop", "ltr_trace_dump",
     "ltr_pinned_alloc", "ltr_pinned_free", "ltr_nccl_unique_id", "ltr_nccl_init", "ltr_nccl_split", "ltr_nccl_info", "ltr_nccl_destroy", "ltr_nccl_version", "ltr_nccl_allreduce_flags",
-    "ltr_nccl_allgather_clouds", "ltr_nccl_exchange_clouds", "ltr_nccl_allgather_i64", "ltr_nccl_max_f64", "ltr_nccl_barrier", "ltr_stream_handle",
+    "ltr_nccl_allgather_clouds", "ltr_nccl_exchange_clouds", "ltr_nccl_voxel_centroid_merged", "ltr_nccl_allgather_i64", "ltr_nccl_max_f64", "ltr_nccl_barrier", "ltr_stream_handle",
 ]
 
 
@@ -118,6 +118,7 @@ def lib():
     L.ltr_nccl_version.argtypes = [P(i32)]
     L.ltr_nccl_allreduce_flags.argtypes = [vp, i32, i32]
     L.ltr_nccl_allgather_clouds.argtypes = [vp, i32, i32, vp, vp]
+    L.ltr_nccl_voxel_centroid_merged.argtypes = [vp, i32, i32, f32, P(i32)]
     L.ltr_nccl_exchange_clouds.argtypes = [vp, i32, i32, i32, vp, i32, vp]
     L.ltr_nccl_allgather_i64.argtypes = [vp, i32, vp, i32, vp]
     L.ltr_nccl_max_f64.argtypes = [vp, i32, ctypes.c_double, P(ctypes.c_double)]

@@ -197,6 +197,47 @@ bool read_pcd(const std::string& path, HostCloud* out, std::string* err) {
             if (col[3] >= 0 && (int)v.size() > col[3]) q.intensity = (float)v[col[3]];
             (*out)[(size_t)i] = q;
         }
+    } else if (data == "binary_compressed") {
+        // pcl::PCDWriter::writeBinaryCompressed: uint32 compressed size, uint32 uncompressed size, LZF stream; the uncompressed payload is
+        // stored field by field (all x, then all y, ...), each field block = points * size * count bytes
+        uint32_t csize = 0, usize = 0;
+        f.read(reinterpret_cast<char*>(&csize), 4); f.read(reinterpret_cast<char*>(&usize), 4);
+        if (!f || usize != (uint64_t)points * (uint64_t)stride) { if (err) *err = "bad binary_compressed sizes in " + path; return false; }
+        std::vector<unsigned char> cbuf(csize), ubuf(usize);
+        f.read(reinterpret_cast<char*>(cbuf.data()), (std::streamsize)csize);
+        if ((size_t)f.gcount() != cbuf.size()) { if (err) *err = "truncated PCD " + path; return false; }
+        {   // LZF decompression (liblzf format: control byte < 32 = literal run of ctrl + 1 bytes, otherwise a back reference)
+            size_t ip = 0, op = 0;
+            while (ip < cbuf.size()) {
+                unsigned ctrl = cbuf[ip++];
+                if (ctrl < 32) {
+                    ++ctrl;
+                    if (ip + ctrl > cbuf.size() || op + ctrl > ubuf.size()) { if (err) *err = "corrupt LZF stream in " + path; return false; }
+                    std::memcpy(&ubuf[op], &cbuf[ip], ctrl);
+                    ip += ctrl; op += ctrl;
+                } else {
+                    size_t len = ctrl >> 5;
+                    if (ip >= cbuf.size()) { if (err) *err = "corrupt LZF stream in " + path; return false; }
+                    if (len == 7) { len += cbuf[ip++]; if (ip >= cbuf.size()) { if (err) *err = "corrupt LZF stream in " + path; return false; } }
+                    const size_t dist = ((size_t)(ctrl & 0x1f) << 8) + cbuf[ip++] + 1;
+                    len += 2;
+                    if (dist > op || op + len > ubuf.size()) { if (err) *err = "corrupt LZF stream in " + path; return false; }
+                    for (size_t t = 0; t < len; ++t, ++op) ubuf[op] = ubuf[op - dist];   // may overlap: byte by byte
+                }
+            }
+            if (op != ubuf.size()) { if (err) *err = "short LZF stream in " + path; return false; }
+        }
+        // field blocks in header order; block start of field i = points * (bytes of the fields before it)
+        for (int j = 0; j < 4; ++j) {
+            if (off[j] < 0) continue;
+            const unsigned char* blk = ubuf.data() + (size_t)points * (size_t)off[j];
+            for (long i = 0; i < points; ++i) {
+                float v;
+                std::memcpy(&v, blk + (size_t)i * 4, 4);
+                PointXYZI& q = (*out)[(size_t)i];
+                (j == 0 ? q.x : j == 1 ? q.y : j == 2 ? q.z : q.intensity) = v;
+            }
+        }
     } else {
         if (err) *err = "unsupported PCD DATA '" + data + "' in " + path;
         return false;

@@ -38,7 +38,7 @@ Mat4 inverse(const Mat4& m);  // general 4x4 inverse, stands in for Eigen::Matri
 
 // ---- PCD ----
 // Reads x, y, z (+ intensity if present) from an ascii or binary PCD with 4-byte float fields (what SC-LIO-SAM /
-// pcl::io::savePCDFileBinary write); other fields are skipped.  binary_compressed is not supported.
+// pcl::io::savePCDFileBinary write); other fields are skipped.  DATA ascii | binary | binary_compressed (LZF, field-major payload).
 bool read_pcd(const std::string& path, HostCloud* out, std::string* err);
 // pcl::io::savePCDFileBinary<PointXYZI>: FIELDS x y z intensity, 16 B/point.  width/height as the reference sets them
 // (octreeDownsampling sets width = 1, height = n, utility.cpp:217-218; everything else width = n, height = 1).

@@ -242,6 +242,23 @@ int Removerter::mergeScansWithinGlobalCoordUtil(Session& s, ltr_scanset scans, l
     return LTR_OK;
 }
 
+int Removerter::mergeAndDownsample(Session& s, ltr_scanset scans, float leaf, ltr_cloud* out) {
+    if (nccl_world >= 0 && group_world > 1) {
+        ltr_cloud m, v;
+        CK(ltr_merge_scans_global(ctx, scans, s.keyframe_poses_, &m));      // this rank's keyframes only
+        const int rc = ltr_nccl_voxel_centroid_merged(ctx, nccl_group[s.id], m, leaf, &v);
+        ltr_cloud_free(ctx, m);
+        if (rc != LTR_OK) return fail(rc, ltr_last_error(ctx));
+        *out = v;
+        return LTR_OK;
+    }
+    ltr_cloud m;
+    CK(mergeScansWithinGlobalCoordUtil(s, scans, &m));
+    CK(octreeDownsampling(&m, leaf));
+    *out = m;
+    return LTR_OK;
+}
+
 int Removerter::precleaningKeyframes(float radius) {
     for (Session* s : {&central_sess_, &query_sess_}) {
         if (!owns(*s)) continue;
@@ -253,11 +270,19 @@ int Removerter::precleaningKeyframes(float radius) {
 }
 
 int Removerter::makeGlobalMap(Session& s) {
-    ltr_cloud orig;
-    CK(mergeScansWithinGlobalCoordUtil(s, s.keyframe_scans_, &orig));       // _sess.mergeScansWithinGlobalCoord() (:218)
-    CK(set(&s.map_global_orig_, orig));
-    ltr_cloud curr;
-    CK(ltr_voxel_centroid(ctx, s.map_global_orig_, P.downsample_voxel_size, &curr));  // :225
+    ltr_cloud orig, curr;
+    if (nccl_world >= 0 && group_world > 1) {
+        // several ranks: the voxelised map comes from the distributed voxeliser (each rank sorts its key range of the ~10^8 raw points);
+        // map_global_orig_ keeps its meaning (the merged raw cloud of ALL keyframes) through a plain gather afterwards
+        CK(ltr_merge_scans_global(ctx, s.keyframe_scans_, s.keyframe_poses_, &orig));       // _sess.mergeScansWithinGlobalCoord() (:218), this rank's keyframes
+        if (ltr_nccl_voxel_centroid_merged(ctx, nccl_group[s.id], orig, P.downsample_voxel_size, &curr) != LTR_OK) return fail(LTR_ERR_CUDA, ltr_last_error(ctx));   // :225
+        CK(gather_cloud(s, &orig));
+        CK(set(&s.map_global_orig_, orig));
+    } else {
+        CK(mergeScansWithinGlobalCoordUtil(s, s.keyframe_scans_, &orig));       // _sess.mergeScansWithinGlobalCoord() (:218)
+        CK(set(&s.map_global_orig_, orig));
+        CK(ltr_voxel_centroid(ctx, s.map_global_orig_, P.downsample_voxel_size, &curr));  // :225
+    }
     CK(set(&s.map_global_curr_, curr));
     CK(save("OriginalNoisy" + s.sess_type_ + "MapGlobal", s.map_global_curr_));       // :231
     return LTR_OK;
@@ -375,10 +400,10 @@ int Removerter::removeHighDynamicPoints() {
         if (owns(C)) CK(extractHighDynPointsViaKnnDiff(C, C.map_global_curr_static_));  // :1591
         if (owns(Q)) CK(extractHighDynPointsViaKnnDiff(Q, Q.map_global_curr_static_));  // :1592
         ltr_cloud c = -1, q = -1;
-        if (owns(C)) CK(mergeScansWithinGlobalCoordUtil(C, C.keyframe_scans_dynamic_, &c));  // :1594
-        if (owns(Q)) CK(mergeScansWithinGlobalCoordUtil(Q, Q.keyframe_scans_dynamic_, &q));  // :1595
-        if (owns(C)) { CK(octreeDownsampling(&c, 0.05f)); CK(save("central_sess_high_dyn", c)); CK(ltr_cloud_free(ctx, c)); }  // :1597, :1600
-        if (owns(Q)) { CK(octreeDownsampling(&q, 0.05f)); CK(save("query_sess_high_dyn", q)); CK(ltr_cloud_free(ctx, q)); }    // :1598, :1601
+        if (owns(C)) CK(mergeAndDownsample(C, C.keyframe_scans_dynamic_, 0.05f, &c));  // :1594, :1597
+        if (owns(Q)) CK(mergeAndDownsample(Q, Q.keyframe_scans_dynamic_, 0.05f, &q));  // :1595, :1598
+        if (owns(C)) { CK(save("central_sess_high_dyn", c)); CK(ltr_cloud_free(ctx, c)); }  // :1600
+        if (owns(Q)) { CK(save("query_sess_high_dyn", q)); CK(ltr_cloud_free(ctx, q)); }    // :1601
     }
     if (split) {
         // Step 2 reads the OTHER session's static map (Removerter.cpp:1416, 1418): hand mine to my partner, take theirs
@@ -416,16 +441,14 @@ int Removerter::extractLowDynPointsViaKnnDiff(Session& s, ltr_cloud target_map) 
 
 int Removerter::constructGlobalNDMap(Session& s) {
     ltr_cloud m;
-    CK(mergeScansWithinGlobalCoordUtil(s, s.scans_knn_diff_, &m));
-    CK(set(&s.map_global_nd_, m));
-    return octreeDownsampling(&s.map_global_nd_, 0.05f);
+    CK(mergeAndDownsample(s, s.scans_knn_diff_, 0.05f, &m));   // Session.cpp:432-434
+    return set(&s.map_global_nd_, m);
 }
 
 int Removerter::constructGlobalPDMap(Session& s) {
     ltr_cloud m;
-    CK(mergeScansWithinGlobalCoordUtil(s, s.scans_knn_diff_, &m));
+    CK(mergeAndDownsample(s, s.scans_knn_diff_, 0.05f, &m));   // Session.cpp:439-441
     CK(set(&s.map_global_pd_, m));
-    CK(octreeDownsampling(&s.map_global_pd_, 0.05f));
     return assign(&s.map_global_pd_orig_, s.map_global_pd_);  // Session.cpp:444
 }
 
@@ -499,23 +522,17 @@ int Removerter::detectLowDynamicPoints() {
     }
     {
         // always-on "save merged maps for visual debug" block (:1442-1480) including its in-place re-downsampling.
-        // The four merges of a rank are gathered with ONE size exchange and ONE grouped transfer.
+        // With several ranks the four merged clouds are voxelised without being gathered (mergeAndDownsample).
         StageTimer t(*this, "ld_merge_viz");
         ltr_cloud qco = -1, cco = -1, qdi = -1, cdi = -1;
-        if (owns(Q)) { CK(ltr_merge_scans_global(ctx, Q.scans_knn_coexist_, Q.keyframe_poses_, &qco)); CK(ltr_merge_scans_global(ctx, Q.scans_knn_diff_, Q.keyframe_poses_, &qdi)); }
-        if (owns(C)) { CK(ltr_merge_scans_global(ctx, C.scans_knn_coexist_, C.keyframe_poses_, &cco)); CK(ltr_merge_scans_global(ctx, C.scans_knn_diff_, C.keyframe_poses_, &cdi)); }
-        if (split) {
-            ltr_cloud* two_q[2] = {&qco, &qdi};
-            ltr_cloud* two_c[2] = {&cco, &cdi};
-            if (owns(Q)) CK(gather_clouds(Q, 2, two_q)); else CK(gather_clouds(C, 2, two_c));
-        } else {
-            ltr_cloud* four[4] = {&qco, &cco, &qdi, &cdi};
-            CK(gather_clouds(C, 4, four));
-        }
-        if (owns(Q)) { CK(octreeDownsampling(&qco, 0.05f)); CK(save("union_map_queryside", qco)); CK(ltr_cloud_free(ctx, qco)); }     // :1443-1446
-        if (owns(C)) { CK(octreeDownsampling(&cco, 0.05f)); CK(save("union_map_centralside", cco)); CK(ltr_cloud_free(ctx, cco)); }   // :1448-1451
-        if (owns(Q)) { CK(octreeDownsampling(&qdi, 0.05f)); CK(save("pd_map", qdi)); CK(ltr_cloud_free(ctx, qdi)); }                  // :1453-1456
-        if (owns(C)) { CK(octreeDownsampling(&cdi, 0.05f)); CK(save("nd_map", cdi)); CK(ltr_cloud_free(ctx, cdi)); }                  // :1458-1461
+        if (owns(Q)) CK(mergeAndDownsample(Q, Q.scans_knn_coexist_, 0.05f, &qco));   // :1443-1444
+        if (owns(C)) CK(mergeAndDownsample(C, C.scans_knn_coexist_, 0.05f, &cco));   // :1448-1449
+        if (owns(Q)) CK(mergeAndDownsample(Q, Q.scans_knn_diff_, 0.05f, &qdi));      // :1453-1454
+        if (owns(C)) CK(mergeAndDownsample(C, C.scans_knn_diff_, 0.05f, &cdi));      // :1458-1459
+        if (owns(Q)) { CK(save("union_map_queryside", qco)); CK(ltr_cloud_free(ctx, qco)); }     // :1446
+        if (owns(C)) { CK(save("union_map_centralside", cco)); CK(ltr_cloud_free(ctx, cco)); }   // :1451
+        if (owns(Q)) { CK(save("pd_map", qdi)); CK(ltr_cloud_free(ctx, qdi)); }                  // :1456
+        if (owns(C)) { CK(save("nd_map", cdi)); CK(ltr_cloud_free(ctx, cdi)); }                  // :1461
         if (owns(Q)) {   // the ND members live where filterStrongND ran
             int64_t n = 0;
             CK(ltr_cloud_size(ctx, C.map_global_nd_strong_, &n));
@@ -534,7 +551,7 @@ int Removerter::updateCurrentMap() {
     Session& C = central_sess_;
     Session& Q = query_sess_;
     ltr_cloud uq = -1, uc = -1, upd = -1, strong = -1;
-    if (owns(Q)) { CK(mergeScansWithinGlobalCoordUtil(Q, Q.scans_knn_coexist_, &uq)); CK(octreeDownsampling(&uq, 0.05f)); }  // :1489-1490
+    if (owns(Q)) CK(mergeAndDownsample(Q, Q.scans_knn_coexist_, 0.05f, &uq));  // :1489-1490
     if (split) {
         // Step 3 runs on the owners of the central keyframes; the query side hands over what it holds of the central session
         if (owns(Q)) {
@@ -549,7 +566,7 @@ int Removerter::updateCurrentMap() {
         CK(set(&C.map_global_nd_weak_, got[1]));
         CK(set(&C.map_global_nd_strong_, got[2]));
     }
-    CK(mergeScansWithinGlobalCoordUtil(C, C.scans_knn_coexist_, &uc)); CK(octreeDownsampling(&uc, 0.05f));  // :1492-1493
+    CK(mergeAndDownsample(C, C.scans_knn_coexist_, 0.05f, &uc));  // :1492-1493
     CK(assign(&upd, uq));                       // :1495
     CK(append(&upd, uc));                       // :1496
     CK(append(&upd, C.map_global_nd_weak_));    // :1500

@@ -80,6 +80,9 @@ public:
     int removeWeakNDMapPointsHavingStrongNDInNear(Session& s);                             // Session.cpp:452-484
     int mergeScansWithinGlobalCoordUtil(Session& s, ltr_scanset scans, ltr_cloud* out);    // utility.cpp:170-192 (+ rank gather)
     int octreeDownsampling(ltr_cloud* cloud, float leaf);                                  // utility.cpp:204-219, in place
+    // mergeScansWithinGlobalCoordUtil followed by octreeDownsampling of the result (the only way the path consumes a merged cloud):
+    // with several ranks the raw merged cloud is never gathered (ltr_nccl_voxel_centroid_merged)
+    int mergeAndDownsample(Session& s, ltr_scanset scans, float leaf, ltr_cloud* out);
 
     // ---- plumbing ----
     int load_session(int sess, const float* xyzi, const int64_t* offsets, const double* poses, const double* inv_poses, int K);

@@ -166,6 +166,13 @@ int stable_partition_by_flag(ltr_ctx* ctx, const DevCloud& in, const uint8_t* fl
 int count_flags(ltr_ctx* ctx, const uint8_t* flags, int64_t n, int64_t* count);
 int exclusive_scan_u32(ltr_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n);  // out[n] elements; returns via out
 int minmax_xyz(ltr_ctx* ctx, const DevCloud& c, float mn[3], float mx[3]);
+// implemented in nccl_comm.cu (internal helpers of the distributed voxeliser in util.cu)
+int nccl_comm_info(ltr_ctx* ctx, int comm, int* rank, int* world);
+int nccl_allreduce_u32(ltr_ctx* ctx, int comm, uint32_t* dev, size_t count, int op /* 0 sum, 1 min, 2 max */);
+// `send` holds this rank's points grouped by destination rank (segment d has scount[d] points, segments back to back); *recv_out
+// receives, in source-rank order, what every rank sent to this one
+int nccl_alltoallv_cloud(ltr_ctx* ctx, int comm, const DevCloud& send, const std::vector<int64_t>& scount, ltr_cloud* recv_out);
+
 int segment_counts(ltr_ctx* ctx, const uint8_t* flags, const DevScanSet& s, std::vector<int64_t>* counts);
 int split_scanset_by_flag(ltr_ctx* ctx, const DevScanSet& in, const uint8_t* flags, ltr_scanset* out_unflagged, ltr_scanset* out_flagged);
 

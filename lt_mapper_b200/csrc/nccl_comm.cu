@@ -92,6 +92,54 @@ static int comm_register(ltr_ctx* ctx, ncclComm_t nc, int rank, int world, int* 
     return LTR_OK;
 }
 
+int nccl_comm_info(ltr_ctx* ctx, int comm, int* rank, int* world) {
+    NcclComm* c;
+    LTR_TRY(comm_get(ctx, comm, &c));
+    *rank = c->rank; *world = c->world;
+    return LTR_OK;
+}
+
+int nccl_allreduce_u32(ltr_ctx* ctx, int comm, uint32_t* dev, size_t count, int op) {
+    NcclComm* c;
+    LTR_TRY(comm_get(ctx, comm, &c));
+    if (c->world <= 1 || count == 0) return LTR_OK;
+    NcclApi* a = nccl_api();
+    LTR_NCCL(ctx, a, a->AllReduce(dev, dev, count, ncclUint32, op == 0 ? ncclSum : op == 1 ? ncclMin : ncclMax, nccl_of(*c), ctx->stream));
+    return LTR_OK;
+}
+
+int nccl_alltoallv_cloud(ltr_ctx* ctx, int comm, const DevCloud& send, const std::vector<int64_t>& scount, ltr_cloud* recv_out) {
+    NcclComm* cp;
+    LTR_TRY(comm_get(ctx, comm, &cp));
+    const NcclComm cc = *cp;
+    const int G = cc.world;
+    if ((int)scount.size() != G || G > 16) return fail(ctx, LTR_ERR_INVALID, "alltoallv: bad count vector");
+    std::vector<int64_t> all((size_t)G * G);
+    LTR_TRY(ltr_nccl_allgather_i64(ctx, comm, scount.data(), G, all.data()));   // all[r * G + d] = points rank r sends to rank d
+    std::vector<int64_t> sdispl((size_t)G + 1, 0), rdispl((size_t)G + 1, 0);
+    for (int d = 0; d < G; ++d) sdispl[d + 1] = sdispl[d] + scount[d];
+    for (int r = 0; r < G; ++r) rdispl[r + 1] = rdispl[r] + all[(size_t)r * G + cc.rank];
+    LTR_TRY(cloud_new(ctx, rdispl[G], recv_out));
+    const DevCloud dst = ctx->clouds[*recv_out];
+    const float* sp[4] = {send.x(), send.y(), send.z(), send.i()};
+    float* dp[4] = {dst.x(), dst.y(), dst.z(), dst.i()};
+    NcclApi* a = nccl_api();
+    LTR_NCCL(ctx, a, a->GroupStart());
+    for (int r = 0; r < G; ++r) {
+        if (r == cc.rank) continue;
+        const int64_t ns = scount[r], nr = all[(size_t)r * G + cc.rank];
+        for (int k = 0; k < 4; ++k) {
+            if (ns > 0) LTR_NCCL(ctx, a, a->Send(sp[k] + sdispl[r], (size_t)ns, ncclFloat32, r, nccl_of(cc), ctx->stream));
+            if (nr > 0) LTR_NCCL(ctx, a, a->Recv(dp[k] + rdispl[r], (size_t)nr, ncclFloat32, r, nccl_of(cc), ctx->stream));
+        }
+    }
+    LTR_NCCL(ctx, a, a->GroupEnd());
+    if (scount[cc.rank] > 0)
+        for (int k = 0; k < 4; ++k)
+            LTR_CUDA(ctx, cudaMemcpyAsync(dp[k] + rdispl[cc.rank], sp[k] + sdispl[cc.rank], (size_t)scount[cc.rank] * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return LTR_OK;
+}
+
 }  // namespace ltr
 
 using namespace ltr;

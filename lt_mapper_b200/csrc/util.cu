@@ -533,14 +533,15 @@ __global__ void __launch_bounds__(256) vox_single_kernel(PtrView c, DevCloud out
 constexpr int64_t kVoxShortcutMin = 100000;   // below this the whole voxelisation is launch-bound and the extra sync does not pay
 
 // `out` must be allocated with cap >= in.n; sets out->n
-static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out) {
+// given_box: the box of a larger cloud this view is a part of (distributed voxelisation); otherwise the box of the view itself
+static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out, const VoxBox* given_box = nullptr) {
     const int64_t n = v.n;
     if (n == 0) { out->n = 0; return LTR_OK; }
     if (!(leaf > 0.0f)) return fail(ctx, LTR_ERR_INVALID, "voxel leaf must be positive");
     if (n >= (int64_t)1 << 31) return fail(ctx, LTR_ERR_UNSUPPORTED, "cloud too large for voxel centroid");
     float mn[3], mx[3];
-    LTR_TRY(minmax_view(ctx, v, mn, mx));
-    const VoxBox b = define_box(mn, mx, leaf);
+    if (!given_box) LTR_TRY(minmax_view(ctx, v, mn, mx));
+    const VoxBox b = given_box ? *given_box : define_box(mn, mx, leaf);
     if (b.depth > 21) return fail(ctx, LTR_ERR_UNSUPPORTED, "octree depth %d > 21 (extent/leaf too large)", b.depth);
     void* p = nullptr;
     ScratchGuard g_p(ctx, &p);
@@ -591,6 +592,153 @@ static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out)
     if (hbad) return fail(ctx, LTR_ERR_UNSUPPORTED, "%u points fall outside the octree bounding box (non-finite coordinates?)", hbad);
     out->n = (int64_t)last[0] + last[1];
     return LTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Distributed voxel centroid: octreeDownsampling (utility.cpp:204-219) of the rank-ordered CONCATENATION of every rank's local
+// cloud, without ever materialising that concatenation.  The merged clouds of the path (utility.cpp:177-189 concatenates the
+// keyframes in order; contiguous keyframe blocks make that the rank order) are only ever consumed through the voxeliser, and
+// gathering 60 M raw points to sort them on every rank was what stopped the multi-GPU step from scaling.
+//   1. global bounding box: ncclAllReduce(min / max) of the ordered-uint encoded local extrema -> the SAME VoxBox as the gathered cloud
+//   2. every rank computes the Morton keys of its local points; a 4096-bin histogram of the key prefixes is all-reduced and cut
+//      into `world` contiguous prefix ranges of (nearly) equal population -- a voxel never straddles a cut
+//   3. one stable radix pass on the destination rank groups the local points by destination; grouped ncclSend/ncclRecv moves
+//      each group to its owner, which receives them in source-rank order == global insertion order
+//   4. the owner voxelises its range with the global box (stable sort + sequential f32 sums: bit-identical to the serial result)
+//   5. the centroid slices (8x fewer points than the input) are all-gathered in range order == octree order.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDistHistBits = 12;
+
+__global__ void __launch_bounds__(256) vox_prefix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&hist[(uint32_t)(keys[i] >> shift)], 1u);     // Morton-ordered or scan-ordered inputs: neighbouring threads mostly hit different bins
+}
+
+struct DestCuts { uint32_t ub[16]; int world; };   // destination of prefix bin b = number of cuts ub[j] (j < world - 1) with b >= ub[j]
+
+__global__ void __launch_bounds__(256) vox_dest_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, DestCuts cuts, uint64_t* __restrict__ dkey,
+                                                       uint32_t* __restrict__ didx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = (uint32_t)(keys[i] >> shift);
+    unsigned d = 0;
+    for (int j = 0; j < cuts.world - 1; ++j) d += (b >= cuts.ub[j]) ? 1u : 0u;
+    dkey[i] = d; didx[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) gather_points_kernel(PtrView in, const uint32_t* __restrict__ idx, DevCloud out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    const uint32_t s = idx[i];
+    out.x()[i] = in.x[s]; out.y()[i] = in.y[s]; out.z()[i] = in.z[s]; out.i()[i] = in.i[s];
+}
+
+static int voxel_distributed(ltr_ctx* ctx, int comm, const DevCloud& loc, float leaf, ltr_cloud* out_h) {
+    int me = 0, G = 1;
+    LTR_TRY(nccl_comm_info(ctx, comm, &me, &G));
+    if (!(leaf > 0.0f)) return fail(ctx, LTR_ERR_INVALID, "voxel leaf must be positive");
+    if (G > 16) return fail(ctx, LTR_ERR_UNSUPPORTED, "distributed voxeliser: more than 16 ranks");
+    const int64_t n = loc.n;
+    if (n >= (int64_t)1 << 31) return fail(ctx, LTR_ERR_UNSUPPORTED, "cloud too large for voxel centroid");
+    // 1. global extrema
+    void* p_mm = nullptr;
+    ScratchGuard g_mm(ctx, &p_mm);
+    LTR_TRY(dev_alloc(ctx, &p_mm, 8 * sizeof(uint32_t) + 2 * ((size_t)1 << kDistHistBits) * sizeof(uint32_t)));
+    uint32_t* d_mm = (uint32_t*)p_mm;
+    uint32_t* d_hist_loc = d_mm + 8;                       // 4096 local, then 4096 global
+    uint32_t* d_hist_glb = d_hist_loc + ((size_t)1 << kDistHistBits);
+    const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    LTR_CUDA(ctx, cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) {
+        const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+        minmax_kernel<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(view(loc), d_mm);
+        LTR_LAUNCH_CHECK(ctx);
+    }
+    LTR_TRY(nccl_allreduce_u32(ctx, comm, d_mm, 3, 1));
+    LTR_TRY(nccl_allreduce_u32(ctx, comm, d_mm + 3, 3, 2));
+    uint32_t h_mm[6];
+    LTR_CUDA(ctx, cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_mm[0] == 0xffffffffu && h_mm[3] == 0u) return cloud_new(ctx, 0, out_h);    // every rank's cloud is empty
+    float mn[3], mx[3];
+    for (int d = 0; d < 3; ++d) { mn[d] = ord2f(h_mm[d]); mx[d] = ord2f(h_mm[3 + d]); }
+    const VoxBox b = define_box(mn, mx, leaf);
+    if (b.depth > 21) return fail(ctx, LTR_ERR_UNSUPPORTED, "octree depth %d > 21 (extent/leaf too large)", b.depth);
+    // 2. local keys + prefix histogram
+    void* p = nullptr;
+    ScratchGuard g_p(ctx, &p);
+    const int64_t nn = std::max<int64_t>(n, 1);
+    LTR_TRY(dev_alloc(ctx, &p, 2 * (size_t)nn * sizeof(uint64_t) + 2 * (size_t)nn * sizeof(uint32_t) + 256));
+    uint64_t* keys0 = (uint64_t*)p;
+    uint64_t* keys1 = keys0 + nn;
+    uint32_t* idx0 = (uint32_t*)(keys1 + nn);
+    uint32_t* idx1 = idx0 + nn;
+    unsigned int* bad = (unsigned int*)(idx1 + nn);
+    LTR_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(unsigned int), ctx->stream));
+    LTR_CUDA(ctx, cudaMemsetAsync(d_hist_loc, 0, 2 * ((size_t)1 << kDistHistBits) * sizeof(uint32_t), ctx->stream));
+    const int hb = std::min(kDistHistBits, 3 * b.depth);
+    const int shift = 3 * b.depth - hb;
+    if (n > 0) {
+        vox_key_kernel<<<(unsigned)((n + kVoxKeyStride - 1) / kVoxKeyStride), 256, 0, ctx->stream>>>(view(loc), b, keys0, idx0, bad, nullptr);
+        LTR_LAUNCH_CHECK(ctx);
+        const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+        vox_prefix_hist_kernel<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(keys0, n, shift, d_hist_loc);
+        LTR_LAUNCH_CHECK(ctx);
+    }
+    LTR_CUDA(ctx, cudaMemcpyAsync(d_hist_glb, d_hist_loc, ((size_t)1 << kDistHistBits) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    LTR_TRY(nccl_allreduce_u32(ctx, comm, d_hist_glb, (size_t)1 << hb, 0));
+    std::vector<uint32_t> h_hist(2 * ((size_t)1 << kDistHistBits));
+    unsigned int hbad = 0;
+    LTR_CUDA(ctx, cudaMemcpyAsync(h_hist.data(), d_hist_loc, h_hist.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaMemcpyAsync(&hbad, bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hbad) return fail(ctx, LTR_ERR_UNSUPPORTED, "%u points fall outside the octree bounding box (non-finite coordinates?)", hbad);
+    const uint32_t* hl = h_hist.data();
+    const uint32_t* hg = h_hist.data() + ((size_t)1 << kDistHistBits);
+    const int nbins = 1 << hb;
+    uint64_t total = 0;
+    for (int i = 0; i < nbins; ++i) total += hg[i];
+    DestCuts cuts;
+    cuts.world = G;
+    {   // cut j = first bin at which the cumulative population reaches (j + 1) / G of the total (identical on every rank: global histogram)
+        uint64_t cum = 0;
+        int j = 0;
+        for (int i = 0; i < nbins && j < G - 1; ++i) {
+            cum += hg[i];
+            while (j < G - 1 && cum * (uint64_t)G >= total * (uint64_t)(j + 1)) cuts.ub[j++] = (uint32_t)(i + 1);
+        }
+        while (j < G - 1) cuts.ub[j++] = (uint32_t)nbins;
+    }
+    std::vector<int64_t> scount((size_t)G, 0);
+    for (int i = 0; i < nbins; ++i) {
+        int d = 0;
+        for (int j = 0; j < G - 1; ++j) d += ((uint32_t)i >= cuts.ub[j]) ? 1 : 0;
+        scount[(size_t)d] += hl[i];
+    }
+    // 3. group the local points by destination (stable), move them to their owners
+    ltr_cloud send_h;
+    LTR_TRY(cloud_new(ctx, n, &send_h));
+    struct CloudGuard { ltr_ctx* c; ltr_cloud h; ~CloudGuard() { if (h >= 0) ltr_cloud_free(c, h); } } g_send{ctx, send_h}, g_recv{ctx, -1}, g_slice{ctx, -1};
+    if (n > 0) {
+        vox_dest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(keys0, n, shift, cuts, keys1, idx1);
+        LTR_LAUNCH_CHECK(ctx);
+        uint64_t* ks; uint32_t* is;
+        LTR_TRY(radix_sort_pairs(ctx, keys1, keys0, idx1, idx0, n, 8, &ks, &is));
+        gather_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(view(loc), is, ctx->clouds[send_h]);
+        LTR_LAUNCH_CHECK(ctx);
+    }
+    g_p.release();
+    LTR_TRY(nccl_alltoallv_cloud(ctx, comm, ctx->clouds[send_h], scount, &g_recv.h));
+    ltr_cloud_free(ctx, send_h); g_send.h = -1;
+    // 4. my range, with the GLOBAL box
+    const DevCloud recv = ctx->clouds[g_recv.h];
+    LTR_TRY(cloud_new(ctx, recv.n, &g_slice.h));
+    DevCloud slice = ctx->clouds[g_slice.h];
+    LTR_TRY(voxel_view(ctx, view(recv), leaf, &slice, &b));
+    ctx->clouds[g_slice.h].n = slice.n;
+    // 5. slices in range order == octree order
+    const ltr_cloud local[1] = {g_slice.h};
+    return ltr_nccl_allgather_clouds(ctx, comm, 1, local, out_h);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -694,6 +842,15 @@ int ltr_voxel_centroid(ltr_ctx* ctx, ltr_cloud in, float leaf, ltr_cloud* out) {
     if (rc != LTR_OK) { cloud_release(ctx, &ctx->clouds[*out]); return rc; }
     ctx->clouds[*out].n = o.n;
     return LTR_OK;
+}
+
+int ltr_nccl_voxel_centroid_merged(ltr_ctx* ctx, int32_t comm, ltr_cloud local, float leaf, ltr_cloud* out) {
+    ApiTrace tr__(ctx, "ltr_nccl_voxel_centroid_merged");
+    if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    DevCloud* c;
+    LTR_TRY(cloud_get(ctx, local, &c));
+    const DevCloud loc = *c;
+    return voxel_distributed(ctx, comm, loc, leaf, out);
 }
 
 int ltr_voxel_centroid_per_keyframe(ltr_ctx* ctx, ltr_scanset in, float leaf, ltr_scanset* out) {

@@ -45,11 +45,20 @@ def classify(ins):
 def main():
     pat = sys.argv[1] if len(sys.argv) > 1 else "map_project_fast_kernelILb1ELb1"
     sass = kernel_sass(pat)
-    # hot window: from the first per-keyframe constant load inside the k loop to the queue-count test after the step
-    starts = [i for i, s in enumerate(sass) if re.match(r"LDCU?(\.64)? .*c\[0x0\]\[U?R\d+\+", s)]
-    first = starts[0] if starts else 0
-    ends = [i for i, s in enumerate(sass) if s.startswith("WARPSYNC") and i > first]
-    last = ends[0] if ends else len(sass)
+    # hot window = one keyframe step of the k loop: the densest cluster of 8 MUFU.RSQ (4 points x 2) marks phase 1; the window runs from
+    # the first register-indexed constant load before it (the per-keyframe constants) to the shared-memory queue test after the step
+    rsq = [i for i, s in enumerate(sass) if s.startswith("MUFU.RSQ")]
+    best = None
+    for a in range(len(rsq) - 7):
+        span = rsq[a + 7] - rsq[a]
+        if best is None or span < best[0]:
+            best = (span, rsq[a], rsq[a + 7])
+    lo, hi = best[1], best[2]
+    first = lo
+    for i in range(lo, max(lo - 120, 0), -1):
+        if re.match(r"LDCU?(\.64)? .*c\[0x0\]\[U?R\d+\+", sass[i]):
+            first = i
+    last = next((i for i in range(hi, len(sass)) if sass[i].startswith("LDS")), len(sass))
     win = sass[first:last]
     # phase 1 = up to the last image gather issued before the first decision branch
     cnt = collections.Counter(classify(s) for s in win)

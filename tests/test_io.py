@@ -112,3 +112,62 @@ def test_yaml_reader_on_the_reference_config():
     assert list(removert.yaml_get(REF_YAML, "removert/remove_resolution_list")[1]) == [2.5]
     assert list(removert.yaml_get(REF_YAML, "removert/ExtrinsicLiDARtoPoseBase")[1]) == list(np.eye(4).ravel())
     assert removert.yaml_get(REF_YAML, "removert/saveMapPCD")[0] == "true"
+
+
+def _lzf_compress(data: bytes) -> bytes:
+    """A valid (not optimal) liblzf stream: greedy back references to the previous occurrence of a 3-byte prefix, literals otherwise."""
+    out = bytearray(); lit = bytearray(); last = {}
+    i, n = 0, len(data)
+
+    def flush():
+        nonlocal lit
+        for s in range(0, len(lit), 32):
+            chunk = lit[s:s + 32]
+            out.append(len(chunk) - 1); out.extend(chunk)
+        lit = bytearray()
+    while i < n:
+        key = data[i:i + 3]
+        ref = last.get(key) if len(key) == 3 else None
+        if ref is not None and 0 < i - ref <= 8192:
+            ln = 3
+            while i + ln < n and ln < 264 and data[ref + ln] == data[i + ln]:
+                ln += 1
+            flush()
+            dist = i - ref - 1
+            l2 = ln - 2
+            if l2 < 7:
+                out.append((l2 << 5) | (dist >> 8))
+            else:
+                out.append((7 << 5) | (dist >> 8)); out.append(l2 - 7)
+            out.append(dist & 0xff)
+            for j in range(i, i + ln):
+                last[data[j:j + 3]] = j
+            i += ln
+        else:
+            last[key] = i
+            lit.append(data[i]); i += 1
+    flush()
+    return bytes(out)
+
+
+def test_pcd_binary_compressed(tmp_path):
+    """pcl::io::loadPCDFile (Session.cpp:275) also accepts DATA binary_compressed: LZF stream of a FIELD-MAJOR payload."""
+    import struct
+    rng = np.random.default_rng(3)
+    n = 5000
+    pts = rng.normal(size=(n, 4)).astype(np.float32)
+    pts[:, 3] = np.repeat(np.arange(n // 50, dtype=np.float32), 50)          # long runs -> back references incl. overlapping ones
+    extra = rng.normal(size=n).astype(np.float32)                            # an extra field between z and intensity is skipped
+    payload = pts[:, 0].tobytes() + pts[:, 1].tobytes() + pts[:, 2].tobytes() + extra.tobytes() + pts[:, 3].tobytes()
+    comp = _lzf_compress(payload)
+    assert len(comp) < len(payload)
+    hdr = (f"# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z ring intensity\nSIZE 4 4 4 4 4\nTYPE F F F F F\nCOUNT 1 1 1 1 1\n"
+           f"WIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\nDATA binary_compressed\n").encode()
+    p = tmp_path / "c.pcd"
+    p.write_bytes(hdr + struct.pack("<II", len(comp), len(payload)) + comp)
+    got = removert.read_pcd(str(p))
+    assert np.array_equal(got.view(np.uint32), pts.view(np.uint32))
+    # truncated stream -> error, not garbage
+    p.write_bytes(hdr + struct.pack("<II", len(comp), len(payload)) + comp[:-7])
+    with pytest.raises(IOError):
+        removert.read_pcd(str(p))
