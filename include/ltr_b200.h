@@ -91,6 +91,9 @@ int ltr_cloud_download(ltr_ctx* ctx, ltr_cloud c, float* xyzi, int64_t capacity,
 int ltr_cloud_free(ltr_ctx* ctx, ltr_cloud c);
 int ltr_cloud_copy(ltr_ctx* ctx, ltr_cloud src, ltr_cloud* out);               /* "*dst = *src" on pcl clouds */
 int ltr_cloud_concat(ltr_ctx* ctx, ltr_cloud a, ltr_cloud b, ltr_cloud* out);  /* "*a += *b" result (Removerter.cpp:902 etc.) */
+/* Non-owning view of the points [begin, end) of `src` (valid while `src` lives; free it like any cloud, nothing is released).  Lets every rank
+ * contribute "its" part of a replicated cloud to ltr_nccl_voxel_centroid_merged. */
+int ltr_cloud_slice(ltr_ctx* ctx, ltr_cloud src, int64_t begin, int64_t end, ltr_cloud* out);
 /* Device pointers of the SoA components (x, y, z, intensity), e.g. for a caller-side collective. */
 int ltr_cloud_device_ptrs(ltr_ctx* ctx, ltr_cloud c, float** x, float** y, float** z, float** i, int64_t* n);
 /* Allocates an uninitialised cloud of n points (to be filled through ltr_cloud_device_ptrs). */

@@ -31,7 +31,7 @@ class Config(ctypes.Structure):
 
 EXPORTS = [
     "ltr_config_default", "ltr_create", "ltr_destroy", "ltr_last_error", "ltr_synchronize", "ltr_kernel_launches", "ltr_voxel_shortcuts", "ltr_memory_stats",
-    "ltr_cloud_upload", "ltr_cloud_size", "ltr_cloud_download", "ltr_cloud_free", "ltr_cloud_copy", "ltr_cloud_concat",
+    "ltr_cloud_upload", "ltr_cloud_size", "ltr_cloud_download", "ltr_cloud_free", "ltr_cloud_copy", "ltr_cloud_concat", "ltr_cloud_slice",
     "ltr_cloud_device_ptrs", "ltr_cloud_alloc", "ltr_scanset_upload", "ltr_scanset_info", "ltr_scanset_download",
     "ltr_scanset_free", "ltr_scanset_concat_per_keyframe", "ltr_scanset_flatten", "ltr_poses_upload", "ltr_poses_free",
     "ltr_preclean", "ltr_merge_scans_global", "ltr_voxel_centroid", "ltr_voxel_centroid_per_keyframe", "ltr_remove_pass",
@@ -73,6 +73,7 @@ def lib():
     L.ltr_cloud_free.argtypes = [vp, i32]
     L.ltr_cloud_copy.argtypes = [vp, i32, P(i32)]
     L.ltr_cloud_concat.argtypes = [vp, i32, i32, P(i32)]
+    L.ltr_cloud_slice.argtypes = [vp, i32, i64, i64, P(i32)]
     L.ltr_cloud_device_ptrs.argtypes = [vp, i32, P(vp), P(vp), P(vp), P(vp), P(i64)]
     L.ltr_scanset_upload.argtypes = [vp, vp, vp, i32, P(i32)]
     L.ltr_scanset_info.argtypes = [vp, i32, P(i32), P(i64)]

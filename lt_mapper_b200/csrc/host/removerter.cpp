@@ -4,6 +4,7 @@
 #include "removerter.h"
 #include "io.h"
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <cstdio>
 
@@ -99,6 +100,7 @@ int Removerter::init() {
     cfg.fast_path = P.fast_path;
     const int rc = ltr_create(&ctx, &cfg);
     if (rc != LTR_OK) err = ltr_last_error(nullptr);
+    if (const char* e = std::getenv("LTR_DIST_VOXEL_MIN")) dist_voxel_min = std::atoll(e);   // tests force the distributed path on small clouds
     return rc;
 }
 
@@ -234,6 +236,21 @@ int Removerter::octreeDownsampling(ltr_cloud* cloud, float leaf) {
     return set(cloud, v);
 }
 
+int Removerter::octreeDownsamplingAppended(ltr_cloud* cloud, float leaf) {
+    int64_t n = 0;
+    CK(ltr_cloud_size(ctx, *cloud, &n));
+    if (!(nccl_world >= 0 && group_world > 1) || n < dist_voxel_min) return octreeDownsampling(cloud, leaf);
+    const int g = nccl_group[0];            // the rank's own group (both entries are the same communicator)
+    int32_t r = 0, w = 1;
+    CK(ltr_nccl_info(ctx, g, &r, &w));
+    ltr_cloud part, v;
+    CK(ltr_cloud_slice(ctx, *cloud, n * r / w, n * (r + 1) / w, &part));
+    const int rc = ltr_nccl_voxel_centroid_merged(ctx, g, part, leaf, &v);
+    ltr_cloud_free(ctx, part);
+    if (rc != LTR_OK) return fail(rc, ltr_last_error(ctx));
+    return set(cloud, v);
+}
+
 int Removerter::mergeScansWithinGlobalCoordUtil(Session& s, ltr_scanset scans, ltr_cloud* out) {
     ltr_cloud m;
     CK(ltr_merge_scans_global(ctx, scans, s.keyframe_poses_, &m));
@@ -316,7 +333,7 @@ int Removerter::removeOnce(Session& t, Session& s, float res) {
     CK(assign(&t.map_global_curr_, t.map_global_curr_static_));    // :899-900
     CK(append(&t.map_global_curr_dynamic_, dy));                   // :902
     CK(ltr_cloud_free(ctx, dy));
-    CK(octreeDownsampling(&t.map_global_curr_dynamic_, 0.05f));    // :903
+    CK(octreeDownsamplingAppended(&t.map_global_curr_dynamic_, 0.05f));    // :903
     CK(ltr_cloud_size(ctx, t.map_global_curr_static_, &log.back().n_static_after));
     CK(ltr_cloud_size(ctx, t.map_global_curr_dynamic_, &log.back().n_dynamic_after));
     return LTR_OK;
@@ -330,7 +347,7 @@ int Removerter::revertOnce(Session& t, Session& s, float res) {
     CK(assign(&t.map_global_curr_, t.map_global_curr_dynamic_));   // :924-925
     CK(append(&t.map_global_curr_static_, st));                    // :927
     CK(ltr_cloud_free(ctx, st));
-    CK(octreeDownsampling(&t.map_global_curr_static_, 0.05f));     // :928
+    CK(octreeDownsamplingAppended(&t.map_global_curr_static_, 0.05f));     // :928
     CK(ltr_cloud_size(ctx, t.map_global_curr_static_, &log.back().n_static_after));
     CK(ltr_cloud_size(ctx, t.map_global_curr_dynamic_, &log.back().n_dynamic_after));
     return LTR_OK;
@@ -678,8 +695,8 @@ int Removerter::cascade_promote_updated() {
     auto grow = [&](void** p, size_t* cap, size_t bytes) {
         if (*cap >= bytes) return true;
         ltr_pinned_free(*p); *p = nullptr; *cap = 0;
-        if (ltr_pinned_alloc(bytes + bytes / 4, p) != LTR_OK) return false;
-        *cap = bytes + bytes / 4;
+        if (ltr_pinned_alloc(2 * bytes, p) != LTR_OK) return false;   // the live scans grow from session to session: leave room
+        *cap = 2 * bytes;
         return true;
     };
     if (!grow(&pin_in_, &pin_in_cap_, (size_t)std::max<int64_t>(total, 1) * 16)) return fail(LTR_ERR_NOMEM, "cascade: pinned staging allocation failed");

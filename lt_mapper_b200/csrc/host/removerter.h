@@ -80,6 +80,9 @@ public:
     int removeWeakNDMapPointsHavingStrongNDInNear(Session& s);                             // Session.cpp:452-484
     int mergeScansWithinGlobalCoordUtil(Session& s, ltr_scanset scans, ltr_cloud* out);    // utility.cpp:170-192 (+ rank gather)
     int octreeDownsampling(ltr_cloud* cloud, float leaf);                                  // utility.cpp:204-219, in place
+    // the same for a freshly appended cloud ("*a += *b", never in octree order): with several ranks every rank contributes its slice of
+    // the (replicated) cloud to the distributed voxeliser, so each sorts 1/G of it instead of all of it
+    int octreeDownsamplingAppended(ltr_cloud* cloud, float leaf);
     // mergeScansWithinGlobalCoordUtil followed by octreeDownsampling of the result (the only way the path consumes a merged cloud):
     // with several ranks the raw merged cloud is never gathered (ltr_nccl_voxel_centroid_merged)
     int mergeAndDownsample(Session& s, ltr_scanset scans, float leaf, ltr_cloud* out);
@@ -111,6 +114,7 @@ public:
     int nccl_world = -1;      // ltr_nccl communicator handles: everyone, ...
     int nccl_group[2] = {-1, -1};   // ... and the ranks that own session s
     int group_world = 1;
+    int64_t dist_voxel_min = 2000000;   // appended clouds below this size are voxelised on every rank (the exchange would cost more than the sort)
     void *pin_in_ = nullptr, *pin_out_ = nullptr;     // page-locked staging of cascade_promote_updated, grown on demand
     size_t pin_in_cap_ = 0, pin_out_cap_ = 0;
     Session central_sess_, query_sess_;

@@ -99,7 +99,7 @@ int cloud_get(ltr_ctx* ctx, ltr_cloud h, DevCloud** c) {
     return LTR_OK;
 }
 void cloud_release(ltr_ctx* ctx, DevCloud* c) {
-    dev_free(ctx, c->base);
+    if (!c->borrowed) dev_free(ctx, c->base);
     dev_free(ctx, c->flags);
     *c = DevCloud();
 }
@@ -386,6 +386,20 @@ int ltr_cloud_copy(ltr_ctx* ctx, ltr_cloud src, ltr_cloud* out) {
     if (sc.n > 0) {
         LTR_CUDA(ctx, cudaMemcpy2DAsync(d.base, (size_t)d.cap * 4, sc.base, (size_t)sc.cap * 4, (size_t)sc.n * 4, 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    return LTR_OK;
+}
+int ltr_cloud_slice(ltr_ctx* ctx, ltr_cloud src, int64_t begin, int64_t end, ltr_cloud* out) {
+    if (!ctx || !out) return fail(ctx, LTR_ERR_INVALID, "null argument");
+    DevCloud* s;
+    LTR_TRY(cloud_get(ctx, src, &s));
+    if (begin < 0 || end < begin || end > s->n) return fail(ctx, LTR_ERR_INVALID, "slice [%lld, %lld) outside [0, %lld)", (long long)begin, (long long)end, (long long)s->n);
+    DevCloud v = *s;
+    v.base = s->base + begin; v.n = end - begin; v.flags = nullptr; v.borrowed = true;   // same component stride (cap)
+    int slot = -1;
+    for (size_t i = 0; i < ctx->clouds.size(); ++i) if (!ctx->clouds[i].used) { slot = (int)i; break; }
+    if (slot < 0) { ctx->clouds.push_back(DevCloud()); slot = (int)ctx->clouds.size() - 1; }
+    ctx->clouds[slot] = v;
+    *out = slot;
     return LTR_OK;
 }
 int ltr_cloud_concat(ltr_ctx* ctx, ltr_cloud a, ltr_cloud b, ltr_cloud* out) {

@@ -16,6 +16,7 @@ struct DevCloud {
     int64_t n = 0, cap = 0;
     uint8_t* flags = nullptr;   // per-point dynamic flags of the last remove pass (lazily allocated, cap bytes)
     bool used = false;
+    bool borrowed = false;      // a view into another cloud's storage (ltr_cloud_slice): releasing it frees nothing
     __host__ __device__ float* x() const { return base; }
     __host__ __device__ float* y() const { return base + cap; }
     __host__ __device__ float* z() const { return base + 2 * cap; }

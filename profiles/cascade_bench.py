@@ -17,7 +17,9 @@ import numpy as np
 # torchrun exports OMP_NUM_THREADS=1 to its children; the host-side pieces here that use OpenMP (synthetic scan generation, the load-time
 # VoxelGrid of a cascade promotion, the reference arm) want this rank's share of the cores.  Must happen before libgomp starts.
 if os.environ.get("OMP_NUM_THREADS", "1") == "1":
-    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))))
+    _w = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    # session split: only the owners of the live session run the host-side VoxelGrid of a promotion, the other half of the ranks is idle then
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // max(1, _w // 2 if _w % 2 == 0 else _w)))
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -26,7 +26,8 @@ def _run(n, out, split, kf=8, cascade=0):
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + 7 * n + split), worker] + args
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    env = dict(os.environ, LTR_DIST_VOXEL_MIN="1000")   # the small pair must exercise the distributed voxelisation of appended clouds too
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     merged = {}
     for f in sorted(glob.glob(os.path.join(out, "rank*.json"))):
