@@ -114,7 +114,10 @@ public:
     int nccl_world = -1;      // ltr_nccl communicator handles: everyone, ...
     int nccl_group[2] = {-1, -1};   // ... and the ranks that own session s
     int group_world = 1;
-    int64_t dist_voxel_min = 2000000;   // appended clouds below this size are voxelised on every rank (the exchange would cost more than the sort)
+    // appended (replicated) clouds of at least this many points go through the distributed voxeliser, every rank contributing a slice.
+    // Off by default: on 4 NVLinked ranks the two size exchanges + the exchange + the gather of a ~10 M point cloud cost more than sorting it on
+    // every rank (hd_remove 115.7 -> 125.5 ms at 8 GPUs, profiles/r02_scaling.md); LTR_DIST_VOXEL_MIN turns it on (the multi-rank tests do).
+    int64_t dist_voxel_min = INT64_MAX;
     void *pin_in_ = nullptr, *pin_out_ = nullptr;     // page-locked staging of cascade_promote_updated, grown on demand
     size_t pin_in_cap_ = 0, pin_out_cap_ = 0;
     Session central_sess_, query_sess_;

@@ -350,9 +350,8 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) map_project_fast
         // Phase 2: decide.  Almost every pair ends at the first comparison.
         if (kDeferred) {
             // 2a: issue the atomics of all four points back to back (their round trips overlap), 2b: use what they returned.
-            // The lanes of a warp hold Morton-neighbours, so several of them usually improve the SAME pixel in the same step; they are
-            // reduced inside the warp first (match.any on the pixel, min over the group) and only the group's nearest pair -- lowest lane
-            // = lowest map index among equal ranges -- goes to memory: the L2 atomic rate, not the arithmetic, bounded this mode.
+            // (Reducing the running minima of a pixel inside the warp first -- match.any on the pixel, redux.min -- was measured slower:
+            // the match costs more than the atomics it saves, profiles/r02_parse_stats.md.)
             unsigned long long old_[kFastPts];
             float rwin_[kFastPts];
             bool enter_[kFastPts], lead_[kFastPts];
@@ -362,18 +361,11 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) map_project_fast
                 // tv = approximate range of the pixel's best pair as read in phase 1 (all-ones bits = NaN while the pixel is empty;
                 // every comparison is written so that NaN means "consider the pair")
                 enter_[j] = certain_[j] && !(fr > __fadd_rn(tv, __fmaf_rn(fc.mr2_rel, fr, fc.mr2_abs)));
-                const bool tried = enter_[j] && !(fr >= tv);            // looks like a new best
-                const unsigned peers = __match_any_sync(0xffffffffu, tried ? pxl_[j] : (0xffffffffu - lane));   // pixels are < 2^18: the others match nobody
-                old_[j] = 0ull; lead_[j] = false; rwin_[j] = tv;
-                if (tried) {
-                    const unsigned rmin = __reduce_min_sync(peers, __float_as_uint(fr));
-                    const unsigned holders = __ballot_sync(peers, __float_as_uint(fr) == rmin);
-                    lead_[j] = (int)lane == __ffs(holders) - 1;
-                    rwin_[j] = __uint_as_float(rmin);
-                    if (lead_[j]) {
-                        const uint32_t mi = (uint32_t)(base + j * 32 < map.n ? base + j * 32 : map.n - 1);
-                        old_[j] = atomicMin(&best_k[pxl_[j]], ((unsigned long long)rmin << 32) | mi);
-                    }
+                lead_[j] = enter_[j] && !(fr >= tv);             // looks like a new best
+                old_[j] = 0ull; rwin_[j] = tv;
+                if (lead_[j]) {
+                    const uint32_t mi = (uint32_t)(base + j * 32 < map.n ? base + j * 32 : map.n - 1);
+                    old_[j] = atomicMin(&best_k[pxl_[j]], ((unsigned long long)__float_as_uint(fr) << 32) | mi);
                 }
             }
 #pragma unroll
