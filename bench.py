@@ -206,19 +206,22 @@ class ReferenceSampler:
       construction: ~3 % of its step), which are left out -- that can only make the reference look faster.
     """
 
-    def __init__(self, kf, S=1, quiet=True):
+    def __init__(self, kf, S=1, sizes=None, synth_kwargs=None):
+        """sizes / synth_kwargs: only tests/test_bench_reference.py passes them (a tiny pair with its own pass-size table)."""
         import synth
         from oracle import ref
         self.ref, self.kf, self.S = ref, kf, S
         self.cores = min(16, os.cpu_count() or 1)      # params_ltmapper.yaml:69 num_omp_cores 16; utility.cpp:109 hard-codes 16 for map2RangeImg
         if not ref.available(omp=True):
             raise RuntimeError("oracle/_ref/libltremovert_ref_omp.so is missing (built by __graft_entry__.build() where /root/reference is mounted)")
-        with open(SIZES_PATH) as f:
-            self.sizes = json.load(f)
+        if sizes is None:
+            with open(SIZES_PATH) as f:
+                sizes = json.load(f)
+        self.sizes = sizes
         if self.sizes["keyframes_per_session"] != kf:
             raise RuntimeError(f"{SIZES_PATH} records {self.sizes['keyframes_per_session']} keyframes/session, asked for {kf}")
         t0 = time.perf_counter()
-        self.data = synth.make_pair(kf)
+        self.data = synth.make_pair(kf, **(synth_kwargs or {}))
         self.params = dict(save_pcd_directory="/tmp/ltr_ref_unused/", sequence_vfov=50.0, sequence_hfov=360.0,
                            ExtrinsicLiDARtoPoseBase=np.eye(4).ravel().tolist(), downsample_voxel_size=0.05, num_nn_points_within=NUM_KNN,
                            dist_nn_points_within=KNN_THR, num_omp_cores=self.cores)

@@ -58,3 +58,41 @@ def test_multi_rank_cascade_equals_single_rank(tmp_path):
     two = _run(2, str(tmp_path / "two"), 1, kf=6, cascade=1)
     bad = [k for k in one if two.get(k) != one[k]]
     assert not bad, bad[:10]
+
+
+def test_standalone_driver_on_two_gpus_writes_the_single_process_tree(tmp_path, small_pair):
+    """apps/ltremovert_b200 started once per GPU (RANK / WORLD_SIZE / LOCAL_RANK, NCCL id through a file -- no Python, no torch in the
+    processes): every rank loads only its keyframe block from disk, and the files written are those of the single-process run."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import filecmp
+    from test_gpu_driver import BIN, _write_session
+    c, q = small_pair
+    _write_session(tmp_path / "central", c)
+    _write_session(tmp_path / "query", q)
+
+    def cfg(out):
+        p = tmp_path / f"params_{out}.yaml"
+        p.write_text("removert:\n  saveMapPCD: true\n" + f'  save_pcd_directory: "{tmp_path / out}"\n'
+                     + f'  central_sess_scan_dir: "{tmp_path}/central/Scans/"\n  central_sess_pose_path: "{tmp_path}/central/poses.txt"\n'
+                     + f'  query_sess_scan_dir: "{tmp_path}/query/Scans/"\n  query_sess_pose_path: "{tmp_path}/query/poses.txt"\n'
+                     + "  sequence_vfov: 50\n  sequence_hfov: 360\n  keyframe_gap: 1\n  start_idx: 0\n  end_idx: 5\n  remove_resolution_list: [2.5, 2.0]\n"
+                     + "  downsample_voxel_size: 0.05\n  num_nn_points_within: 2\n  dist_nn_points_within: 0.01\n")
+        return str(p)
+    r = subprocess.run([BIN, "--config", cfg("one"), "--selfremovert"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for mode, extra in (("two_split", []), ("two_blocks", ["--no-split"])):
+        procs = []
+        for rank in range(2):
+            env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_PORT="29601", LTR_NCCL_ID_FILE=str(tmp_path / f"id_{mode}"),
+                       LTR_DIST_VOXEL_MIN="1000")
+            procs.append(subprocess.Popen([BIN, "--config", cfg(mode), "--selfremovert"] + extra, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+        def tree(d):
+            return sorted(os.path.relpath(os.path.join(p, f), d) for p, _, fs in os.walk(d) for f in fs)
+        files = tree(tmp_path / "one")
+        assert files == tree(tmp_path / mode) and len(files) >= 14 + 5 * 3, (mode, sorted(set(files) ^ set(tree(tmp_path / mode))))
+        for f in files:
+            assert filecmp.cmp(tmp_path / "one" / f, tmp_path / mode / f, shallow=False), (mode, f)

@@ -171,3 +171,11 @@ def test_pcd_binary_compressed(tmp_path):
     p.write_bytes(hdr + struct.pack("<II", len(comp), len(payload)) + comp[:-7])
     with pytest.raises(IOError):
         removert.read_pcd(str(p))
+
+
+def test_inverse_poses_is_the_cofactor_inverse_of_the_oracle():
+    """ltrh_invert_poses == the oracle's / reference shim's Eigen::Matrix4d::inverse() stand-in, bit for bit (an LU inverse is not)."""
+    import oracle
+    import synth
+    d = synth.make_session(1, 64, beams=4, az_steps=8)
+    assert np.array_equal(removert.inverse_poses(d.poses), oracle.inverse_poses(d.poses))
