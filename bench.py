@@ -83,7 +83,7 @@ class ClockSampler:
     calling nvmlDeviceGetClockInfo / nvmlDeviceGetCurrentClocksEventReasons; `nvidia-smi -lms` was measured to slow the
     launch-heavy step by ~30 % through driver-lock contention, direct NVML calls do not)."""
 
-    def __init__(self, gpu_index, period_s=0.25):
+    def __init__(self, gpu_index, period_s=0.1):
         self.gpu, self.period, self.rows, self.stop_flag, self.thread, self.err = gpu_index, period_s, [], False, None, None
 
     def start(self):

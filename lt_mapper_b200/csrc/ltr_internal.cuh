@@ -1,6 +1,7 @@
 // Internal context / device-container definitions shared by the translation units of libltr_b200.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler (nsys, ncu --nvtx) is attached
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -115,7 +116,7 @@ int fail(ltr_ctx* ctx, int code, const char* fmt, ...);
                                                    cudaGetErrorString(e__), __FILE__, __LINE__);      \
     } while (0)
 
-// Entry-point guard: makes the context's GPU the calling thread's current device for the duration of the call (the caller may have
+// Entry-point guard: opens an NVTX range, makes the context's GPU the calling thread's current device for the duration of the call (the caller may have
 // switched devices -- torch.cuda.set_device, a second context on another GPU -- and cudaMalloc / kernel launches follow the CURRENT
 // device) and restores the previous one afterwards; with LTR_TRACE=1 it also times the call on the host between two stream
 // synchronisations.
@@ -123,12 +124,14 @@ struct ApiTrace {
     ltr_ctx* c; const char* name; double t0; int prev_dev = -1;
     static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
     ApiTrace(ltr_ctx* ctx, const char* n) : c(ctx), name(n), t0(0) {
+        nvtxRangePushA(n);            // every C-ABI entry point is an NVTX range named after itself
         if (!c) return;
         int cur = -1;
         if (cudaGetDevice(&cur) == cudaSuccess && cur != c->device) { prev_dev = cur; cudaSetDevice(c->device); }
         if (c->trace) { cudaStreamSynchronize(c->stream); t0 = now(); }
     }
     ~ApiTrace() {
+        nvtxRangePop();
         if (!c) return;
         if (c->trace) { cudaStreamSynchronize(c->stream); auto& a = c->trace_acc[name]; a.first += now() - t0; a.second += 1; }
         if (prev_dev >= 0) cudaSetDevice(prev_dev);
