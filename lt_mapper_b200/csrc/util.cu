@@ -253,12 +253,15 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const uint64_t* __r
     hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = s_hist[threadIdx.x];
 }
 
+// kVals = false: keys only (the voxeliser packs the point index into the low bits of the key whenever both fit 64 bits: 8 instead of
+// 12 bytes per element and pass, 32 instead of 48 KB of shared memory per tile)
+template <bool kVals>
 __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                                                                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                                                                 const uint32_t* __restrict__ offs, int ntiles) {
     // dynamic shared memory: the tile's keys and values in their sorted-by-digit order, so that the global writes of a digit bucket
     // are one contiguous, coalesced run instead of 8-byte scatters
-    extern __shared__ uint64_t s_keys[];                            // kRsTile keys, then kRsTile values
+    extern __shared__ uint64_t s_keys[];                            // kRsTile keys, then (kVals) kRsTile values
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + kRsTile);
     __shared__ uint32_t s_cnt[kRsThreads / 32][256];
     __shared__ uint32_t s_excl[256];     // exclusive prefix of the tile's digit counts (position of the bucket inside the tile)
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t* 
             const unsigned d = (unsigned)(key[r] >> shift) & 255u;
             const uint32_t lp = s_excl[d] + s_cnt[warp][d] + rank[r];
             s_keys[lp] = key[r];
-            s_vals[lp] = vals_in[i];
+            if (kVals) s_vals[lp] = vals_in[i];
         }
     }
     __syncthreads();
@@ -319,19 +322,23 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const uint64_t* 
         const uint64_t k = s_keys[t];
         const uint32_t pos = s_gdelta[(unsigned)(k >> shift) & 255u] + (uint32_t)t;
         keys_out[pos] = k;
-        vals_out[pos] = s_vals[t];
+        if (kVals) vals_out[pos] = s_vals[t];
     }
 }
 
 constexpr size_t kRsScatterSmem = (size_t)kRsTile * (sizeof(uint64_t) + sizeof(uint32_t));   // 48 KB: needs the opt-in above 48 KB - 0
+constexpr size_t kRsScatterSmemKeys = (size_t)kRsTile * sizeof(uint64_t);                     // 32 KB
 
-// Sorts (keys0, vals0) using (keys1, vals1) as the other half of the ping-pong; *keys_sorted / *vals_sorted point at the result.
-static int radix_sort_pairs(ltr_ctx* ctx, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, int64_t n, int key_bits,
+// Sorts (keys0, vals0) on the key bits [bit_lo, bit_hi) using (keys1, vals1) as the other half of the ping-pong; *keys_sorted /
+// *vals_sorted point at the result.  vals0 == nullptr: keys only.
+static int radix_sort_pairs(ltr_ctx* ctx, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, int64_t n, int bit_lo, int bit_hi,
                             uint64_t** keys_sorted, uint32_t** vals_sorted) {
-    *keys_sorted = keys0; *vals_sorted = vals0;
-    if (n <= 1 || key_bits <= 0) return LTR_OK;
-    if (!ctx->rs_attr_set) {   // 48 KB dynamic + ~10 KB static shared memory: above the default 48 KB limit (per device)
-        LTR_CUDA(ctx, cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsScatterSmem));
+    *keys_sorted = keys0;
+    if (vals_sorted) *vals_sorted = vals0;
+    if (n <= 1 || bit_hi <= bit_lo) return LTR_OK;
+    const bool with_vals = vals0 != nullptr;
+    if (with_vals && !ctx->rs_attr_set) {   // 48 KB dynamic + ~10 KB static shared memory: above the default 48 KB limit (per device)
+        LTR_CUDA(ctx, cudaFuncSetAttribute(rs_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsScatterSmem));
         ctx->rs_attr_set = true;
     }
     const int ntiles = (int)((n + kRsTile - 1) / kRsTile);
@@ -341,19 +348,21 @@ static int radix_sort_pairs(ltr_ctx* ctx, uint64_t* keys0, uint64_t* keys1, uint
     uint32_t* hist = (uint32_t*)p;
     uint64_t *kin = keys0, *kout = keys1;
     uint32_t *vin = vals0, *vout = vals1;
-    for (int shift = 0; shift < key_bits; shift += 8) {
+    for (int shift = bit_lo; shift < bit_hi; shift += 8) {
         rs_hist_kernel<<<ntiles, kRsThreads, 0, ctx->stream>>>(kin, n, shift, hist, ntiles);
         LTR_LAUNCH_CHECK(ctx);
         if ((int64_t)256 * ntiles <= 1024 * 64) {   // small matrix: one block scans it (also writes the total past the end, hence the + 1 above)
             scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(hist, hist, 256 * ntiles);
             LTR_LAUNCH_CHECK(ctx);
         } else LTR_TRY(exclusive_scan_u32(ctx, hist, hist, (int64_t)256 * ntiles));
-        rs_scatter_kernel<<<ntiles, kRsThreads, kRsScatterSmem, ctx->stream>>>(kin, kout, vin, vout, n, shift, hist, ntiles);
+        if (with_vals) rs_scatter_kernel<true><<<ntiles, kRsThreads, kRsScatterSmem, ctx->stream>>>(kin, kout, vin, vout, n, shift, hist, ntiles);
+        else rs_scatter_kernel<false><<<ntiles, kRsThreads, kRsScatterSmemKeys, ctx->stream>>>(kin, kout, nullptr, nullptr, n, shift, hist, ntiles);
         LTR_LAUNCH_CHECK(ctx);
         std::swap(kin, kout); std::swap(vin, vout);
     }
     g_p.release();
-    *keys_sorted = kin; *vals_sorted = vin;
+    *keys_sorted = kin;
+    if (vals_sorted) *vals_sorted = vin;
     return LTR_OK;
 }
 
@@ -466,7 +475,8 @@ __device__ __forceinline__ uint64_t vox_code(const PtrView& c, const VoxBox& b, 
 // overlap by one point (block b covers points b*255 .. b*255+255) so that every point finds its predecessor's code inside its own
 // block -- through the neighbouring lane or shared memory -- without a divergent recomputation of the f64 divisions.
 constexpr int kVoxKeyStride = 255;
-__global__ void __launch_bounds__(256) vox_key_kernel(PtrView c, VoxBox b, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx,
+// idx == nullptr: packed mode, keys[i] = code << pack_shift | i (the caller checked that both fit 64 bits)
+__global__ void __launch_bounds__(256) vox_key_kernel(PtrView c, VoxBox b, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx, int pack_shift,
                                                       unsigned int* __restrict__ bad, unsigned int* __restrict__ unsorted) {
     __shared__ uint64_t s_last[8];   // code of lane 31 of each warp
     const int64_t i = (int64_t)blockIdx.x * kVoxKeyStride + threadIdx.x;
@@ -478,8 +488,8 @@ __global__ void __launch_bounds__(256) vox_key_kernel(PtrView c, VoxBox b, uint6
         key = vox_code(c, b, i, &inside);
         if (owner) {
             if (!inside) atomicAdd(bad, 1u);
-            keys[i] = key;
-            idx[i] = (uint32_t)i;
+            if (idx) { keys[i] = key; idx[i] = (uint32_t)i; }
+            else keys[i] = (key << pack_shift) | (uint64_t)i;
         }
     }
     if (unsorted) {
@@ -494,27 +504,31 @@ __global__ void __launch_bounds__(256) vox_key_kernel(PtrView c, VoxBox b, uint6
     }
 }
 
-__global__ void __launch_bounds__(256) vox_head_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ head) {
+__global__ void __launch_bounds__(256) vox_head_kernel(const uint64_t* __restrict__ keys, int pack_shift, int64_t n, uint32_t* __restrict__ head) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+    head[i] = (i == 0 || (keys[i] >> pack_shift) != (keys[i - 1] >> pack_shift)) ? 1u : 0u;
 }
 
 // one thread per voxel: find its run [start, end) and sum sequentially in sorted (== insertion) order
-__global__ void __launch_bounds__(256) vox_centroid_kernel(PtrView c, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idx,
+__global__ void __launch_bounds__(256) vox_centroid_kernel(PtrView c, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idx, int pack_shift,
                                                            const uint32_t* __restrict__ head, const uint32_t* __restrict__ rank, int64_t n,
                                                            DevCloud out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !head[i]) return;
-    const uint64_t key = keys[i];
+    const uint64_t idx_mask = ((uint64_t)1 << pack_shift) - 1;
+    uint64_t kj = keys[i];
+    const uint64_t code = kj >> pack_shift;
     float sx = 0.0f, sy = 0.0f, sz = 0.0f, si = 0.0f;
     int64_t j = i;
     int cnt = 0;
     do {
-        const uint32_t p = idx[j];
+        const uint32_t p = idx ? idx[j] : (uint32_t)(kj & idx_mask);
         sx = fa(sx, c.x[p]); sy = fa(sy, c.y[p]); sz = fa(sz, c.z[p]); si = fa(si, c.i[p]);
         ++cnt; ++j;
-    } while (j < n && keys[j] == key);
+        if (j >= n) break;
+        kj = keys[j];
+    } while ((kj >> pack_shift) == code);
     const float fc = (float)cnt;
     const uint32_t o = rank[i];
     out.x()[o] = fd(sx, fc); out.y()[o] = fd(sy, fc); out.z()[o] = fd(sz, fc); out.i()[o] = fd(si, fc);
@@ -546,12 +560,18 @@ static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out,
     void* p = nullptr;
     ScratchGuard g_p(ctx, &p);
     const size_t kb = (size_t)n * sizeof(uint64_t), ib = (size_t)n * sizeof(uint32_t);
-    LTR_TRY(dev_alloc(ctx, &p, 2 * kb + 4 * ib + 256));
+    // the point index rides in the low bits of the sort key when Morton code + index fit 64 bits (every cloud of the path: depth <= 12,
+    // n < 2^28); the stable sort then moves 8-byte keys only and still leaves equal codes in insertion order
+    int idx_bits = 1;
+    while (idx_bits < 32 && ((int64_t)1 << idx_bits) < n) ++idx_bits;
+    const bool packed = 3 * b.depth + idx_bits <= 64;
+    const int pack_shift = packed ? idx_bits : 0;
+    LTR_TRY(dev_alloc(ctx, &p, 2 * kb + (packed ? 2 : 4) * ib + 256));
     uint64_t* keys0 = (uint64_t*)p;
     uint64_t* keys1 = keys0 + n;
-    uint32_t* idx0 = (uint32_t*)(keys1 + n);
-    uint32_t* idx1 = idx0 + n;
-    uint32_t* head = idx1 + n;
+    uint32_t* idx0 = packed ? nullptr : (uint32_t*)(keys1 + n);
+    uint32_t* idx1 = packed ? nullptr : idx0 + n;
+    uint32_t* head = packed ? (uint32_t*)(keys1 + n) : idx1 + n;
     uint32_t* rank = head + n;
     unsigned int* bad = (unsigned int*)(rank + n);
     LTR_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(unsigned int), ctx->stream));
@@ -559,7 +579,7 @@ static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out,
     const unsigned nb = (unsigned)((n + T - 1) / T);
     const bool try_shortcut = n >= kVoxShortcutMin;
     LTR_CUDA(ctx, cudaMemsetAsync(bad + 1, 0, sizeof(unsigned int), ctx->stream));
-    vox_key_kernel<<<(unsigned)((n + kVoxKeyStride - 1) / kVoxKeyStride), T, 0, ctx->stream>>>(v, b, keys0, idx0, bad, try_shortcut ? bad + 1 : nullptr);
+    vox_key_kernel<<<(unsigned)((n + kVoxKeyStride - 1) / kVoxKeyStride), T, 0, ctx->stream>>>(v, b, keys0, idx0, pack_shift, bad, try_shortcut ? bad + 1 : nullptr);
     LTR_LAUNCH_CHECK(ctx);
     if (try_shortcut) {
         unsigned int h[2] = {0, 1};
@@ -576,11 +596,11 @@ static int voxel_view(ltr_ctx* ctx, const PtrView& v, float leaf, DevCloud* out,
         }
     }
     uint64_t* keys_s; uint32_t* idx_s;
-    LTR_TRY(radix_sort_pairs(ctx, keys0, keys1, idx0, idx1, n, 3 * b.depth, &keys_s, &idx_s));
-    vox_head_kernel<<<nb, T, 0, ctx->stream>>>(keys_s, n, head);
+    LTR_TRY(radix_sort_pairs(ctx, keys0, keys1, idx0, idx1, n, pack_shift, pack_shift + 3 * b.depth, &keys_s, &idx_s));
+    vox_head_kernel<<<nb, T, 0, ctx->stream>>>(keys_s, pack_shift, n, head);
     LTR_LAUNCH_CHECK(ctx);
     LTR_TRY(exclusive_scan_u32(ctx, head, rank, n));
-    vox_centroid_kernel<<<nb, T, 0, ctx->stream>>>(v, keys_s, idx_s, head, rank, n, *out);
+    vox_centroid_kernel<<<nb, T, 0, ctx->stream>>>(v, keys_s, idx_s, pack_shift, head, rank, n, *out);
     LTR_LAUNCH_CHECK(ctx);
     uint32_t last[2];
     unsigned int hbad = 0;
@@ -679,7 +699,7 @@ static int voxel_distributed(ltr_ctx* ctx, int comm, const DevCloud& loc, float 
     const int hb = std::min(kDistHistBits, 3 * b.depth);
     const int shift = 3 * b.depth - hb;
     if (n > 0) {
-        vox_key_kernel<<<(unsigned)((n + kVoxKeyStride - 1) / kVoxKeyStride), 256, 0, ctx->stream>>>(view(loc), b, keys0, idx0, bad, nullptr);
+        vox_key_kernel<<<(unsigned)((n + kVoxKeyStride - 1) / kVoxKeyStride), 256, 0, ctx->stream>>>(view(loc), b, keys0, idx0, 0, bad, nullptr);
         LTR_LAUNCH_CHECK(ctx);
         const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
         vox_prefix_hist_kernel<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(keys0, n, shift, d_hist_loc);
@@ -723,7 +743,7 @@ static int voxel_distributed(ltr_ctx* ctx, int comm, const DevCloud& loc, float 
         vox_dest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(keys0, n, shift, cuts, keys1, idx1);
         LTR_LAUNCH_CHECK(ctx);
         uint64_t* ks; uint32_t* is;
-        LTR_TRY(radix_sort_pairs(ctx, keys1, keys0, idx1, idx0, n, 8, &ks, &is));
+        LTR_TRY(radix_sort_pairs(ctx, keys1, keys0, idx1, idx0, n, 0, 8, &ks, &is));
         gather_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(view(loc), is, ctx->clouds[send_h]);
         LTR_LAUNCH_CHECK(ctx);
     }
