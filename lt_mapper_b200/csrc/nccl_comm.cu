@@ -317,10 +317,10 @@ int ltr_nccl_exchange_clouds(ltr_ctx* ctx, int32_t comm, int32_t peer, int32_t n
     if (n_send > 0) LTR_NCCL(ctx, a, a->Send(d, (size_t)n_send, ncclInt64, peer, nccl_of(cc), ctx->stream));
     if (n_recv > 0) LTR_NCCL(ctx, a, a->Recv(d + kMaxBatch, (size_t)n_recv, ncclInt64, peer, nccl_of(cc), ctx->stream));
     LTR_NCCL(ctx, a, a->GroupEnd());
-    if (n_recv > 0) {
-        LTR_CUDA(ctx, cudaMemcpyAsync(h + kMaxBatch, d + kMaxBatch, sizeof(int64_t) * (size_t)n_recv, cudaMemcpyDeviceToHost, ctx->stream));
-        LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    if (n_recv > 0) LTR_CUDA(ctx, cudaMemcpyAsync(h + kMaxBatch, d + kMaxBatch, sizeof(int64_t) * (size_t)n_recv, cudaMemcpyDeviceToHost, ctx->stream));
+    // also on a send-only side: the pinned staging slots h[0, n_send) are reused by the next count exchange on this communicator,
+    // which must not overwrite them before the asynchronous upload above has read them
+    LTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < n_recv; ++i) LTR_TRY(cloud_new(ctx, h[kMaxBatch + i], &recv[i]));
     LTR_NCCL(ctx, a, a->GroupStart());
     for (int i = 0; i < n_send; ++i) {
