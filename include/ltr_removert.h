@@ -122,6 +122,10 @@ int32_t ltrh_io_parse_keyframes(int32_t num_scans, int32_t start_idx, int32_t en
 int32_t ltrh_io_parse_keyframes_in_roi(const double* scan_poses16, int32_t n, const double* roi_poses16, int32_t m, int32_t gap, int32_t* out, int32_t capacity);
 /* pcl::VoxelGrid at load (Session.cpp:284-289) incl. the int32 overflow fallback that returns the input unchanged */
 int64_t ltrh_io_voxel_grid(const float* xyzi, int64_t n, float leaf, float* out, int64_t capacity, int32_t* overflowed);
+/* the same filter over the K scans of a session held back to back (scan k = points [off[k], off[k+1])), scans on different OpenMP
+ * threads (Session::loadKeyframes' loop, Session.cpp:272-303).  Returns the total number of output points and fills out_off[K + 1];
+ * `out` is written only if capacity (points) suffices. */
+int64_t ltrh_io_voxel_grid_scans(const float* xyzi, const int64_t* off, int32_t K, float leaf, float* out, int64_t capacity, int64_t* out_off);
 /* one key of a roslaunch-style yaml ("removert/key"): scalar text and/or numeric list */
 int ltrh_io_yaml_get(const char* path, const char* key, char* value, int32_t capacity, double* list, int32_t list_capacity, int32_t* list_n);
 

@@ -259,21 +259,19 @@ bool write_pcd_binary(const std::string& path, const HostCloud& c, bool octree_l
 }
 
 // ------------------------------------------------------------------------------------------------ pcl::VoxelGrid
-HostCloud voxel_grid(const HostCloud& in, float leaf, bool* overflowed) {
-    if (overflowed) *overflowed = false;
-    if (in.empty()) return in;
+// Core of the filter on a span of points.  Returns false when PCL takes its overflow exit ("Leaf size is too small for the input
+// dataset": output = *input_); `out` is then left untouched so that callers can pass the input through without a copy.
+static bool voxel_grid_span(const PointXYZI* in, size_t n, float leaf, HostCloud* out) {
     const float inv = 1.0f / leaf;  // inverse_leaf_size_ = Ones / leaf_size_
     float mn[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
     float mx[3] = {-mn[0], -mn[1], -mn[2]};
-    for (const auto& p : in) {
+    for (size_t i = 0; i < n; ++i) {
+        const PointXYZI& p = in[i];
         mn[0] = std::min(mn[0], p.x); mn[1] = std::min(mn[1], p.y); mn[2] = std::min(mn[2], p.z);
         mx[0] = std::max(mx[0], p.x); mx[1] = std::max(mx[1], p.y); mx[2] = std::max(mx[2], p.z);
     }
     const int64_t dx = (int64_t)((mx[0] - mn[0]) * inv) + 1, dy = (int64_t)((mx[1] - mn[1]) * inv) + 1, dz = (int64_t)((mx[2] - mn[2]) * inv) + 1;
-    if (dx * dy * dz > (int64_t)std::numeric_limits<int32_t>::max()) {  // "Leaf size is too small for the input dataset"
-        if (overflowed) *overflowed = true;
-        return in;                                                      // output = *input_
-    }
+    if (dx * dy * dz > (int64_t)std::numeric_limits<int32_t>::max()) return false;
     int min_b[3], max_b[3], div_b[3];
     for (int d = 0; d < 3; ++d) { min_b[d] = (int)std::floor(mn[d] * inv); max_b[d] = (int)std::floor(mx[d] * inv); div_b[d] = max_b[d] - min_b[d] + 1; }
     const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
@@ -282,15 +280,15 @@ HostCloud voxel_grid(const HostCloud& in, float leaf, bool* overflowed) {
         bool operator<(const cloud_point_index_idx& p) const { return idx < p.idx; }
     };
     std::vector<cloud_point_index_idx> iv;
-    iv.reserve(in.size());
-    for (size_t i = 0; i < in.size(); ++i) {
+    iv.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
         const int ijk0 = (int)(std::floor(in[i].x * inv) - (float)min_b[0]);
         const int ijk1 = (int)(std::floor(in[i].y * inv) - (float)min_b[1]);
         const int ijk2 = (int)(std::floor(in[i].z * inv) - (float)min_b[2]);
         iv.push_back({(unsigned int)(ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2]), (unsigned int)i});
     }
     std::sort(iv.begin(), iv.end(), std::less<cloud_point_index_idx>());
-    HostCloud out;
+    out->clear();
     size_t i = 0;
     while (i < iv.size()) {
         size_t j = i;
@@ -300,11 +298,49 @@ HostCloud voxel_grid(const HostCloud& in, float leaf, bool* overflowed) {
             sx += p.x; sy += p.y; sz += p.z; si += p.intensity;   // CentroidPoint accumulators (float)
             ++j;
         }
-        const float n = (float)(j - i);
-        out.push_back({sx / n, sy / n, sz / n, si / n});
+        const float cnt = (float)(j - i);
+        out->push_back({sx / cnt, sy / cnt, sz / cnt, si / cnt});
         i = j;
     }
+    return true;
+}
+
+HostCloud voxel_grid(const HostCloud& in, float leaf, bool* overflowed) {
+    if (overflowed) *overflowed = false;
+    if (in.empty()) return in;
+    HostCloud out;
+    if (!voxel_grid_span(in.data(), in.size(), leaf, &out)) {
+        if (overflowed) *overflowed = true;
+        return in;                                                      // output = *input_
+    }
     return out;
+}
+
+void VoxelGridBatch::plan(const float* xyzi, const int64_t* off, int K, float leaf) {
+    static_assert(sizeof(PointXYZI) == 4 * sizeof(float), "PointXYZI must be four packed floats");
+    const PointXYZI* pts = reinterpret_cast<const PointXYZI*>(xyzi);
+    grids.assign((size_t)K, HostCloud());
+    unchanged.assign((size_t)K, 0);
+    out_off.assign((size_t)K + 1, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int k = 0; k < K; ++k) {
+        const size_t n = (size_t)(off[k + 1] - off[k]);
+        if (n == 0 || !voxel_grid_span(pts + off[k], n, leaf, &grids[(size_t)k])) unchanged[(size_t)k] = 1;
+    }
+    for (int k = 0; k < K; ++k)
+        out_off[(size_t)k + 1] = out_off[(size_t)k] + (unchanged[(size_t)k] ? off[k + 1] - off[k] : (int64_t)grids[(size_t)k].size());
+}
+
+void VoxelGridBatch::emit(const float* xyzi, const int64_t* off, float* out) const {
+    const int K = (int)grids.size();
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int k = 0; k < K; ++k) {
+        float* o = out + (size_t)out_off[(size_t)k] * 4;
+        const size_t n = (size_t)(out_off[(size_t)k + 1] - out_off[(size_t)k]);
+        if (n == 0) continue;
+        if (unchanged[(size_t)k]) std::memcpy(o, xyzi + (size_t)off[k] * 4, n * sizeof(PointXYZI));
+        else std::memcpy(o, grids[(size_t)k].data(), n * sizeof(PointXYZI));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ sessions

@@ -49,6 +49,17 @@ bool write_pcd_binary(const std::string& path, const HostCloud& c, bool octree_l
 // (dx*dy*dz) > INT32_MAX, which is the common case for 0.05 m leaves on outdoor scans; otherwise voxel index sort
 // (std::sort on idx, as PCL) and float centroid accumulation in sorted order.
 HostCloud voxel_grid(const HostCloud& in, float leaf, bool* overflowed);
+// The same filter over the K scans of a session held back to back (interleaved x y z intensity, scan k = points
+// [off[k], off[k+1])): what Session::loadKeyframes does scan by scan (Session.cpp:272-303).  Two phases so that the caller can
+// size (page-locked) destination memory in between; scans run on different OpenMP threads, and a scan that takes PCL's
+// overflow exit is passed through with one memcpy instead of being rebuilt point by point.
+struct VoxelGridBatch {
+    std::vector<HostCloud> grids;       // filtered scans (empty for pass-through scans)
+    std::vector<uint8_t> unchanged;     // 1: overflow exit (or empty scan), output = input
+    std::vector<int64_t> out_off;       // K + 1 point offsets of the result
+    void plan(const float* xyzi, const int64_t* off, int K, float leaf);
+    void emit(const float* xyzi, const int64_t* off, float* out) const;   // out: out_off[K] points
+};
 
 // ---- session bookkeeping ----
 struct SessionFiles {

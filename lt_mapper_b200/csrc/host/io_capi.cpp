@@ -49,6 +49,16 @@ int64_t ltrh_io_voxel_grid(const float* xyzi, int64_t n, float leaf, float* out,
     if ((int64_t)o.size() <= capacity && !o.empty()) std::memcpy(out, o.data(), o.size() * sizeof(PointXYZI));
     return (int64_t)o.size();
 }
+// all K scans of a session at once (VoxelGridBatch): returns the total number of output points and fills out_off[K + 1];
+// `out` is written only when it is large enough (call with capacity 0 first to size it)
+int64_t ltrh_io_voxel_grid_scans(const float* xyzi, const int64_t* off, int32_t K, float leaf, float* out, int64_t capacity, int64_t* out_off) {
+    if (K < 0 || !off || (K > 0 && !xyzi && off[K] > 0)) return -1;
+    VoxelGridBatch b;
+    b.plan(xyzi, off, K, leaf);
+    if (out_off) for (int k = 0; k <= K; ++k) out_off[k] = b.out_off[(size_t)k];
+    if (out && b.out_off[(size_t)K] <= capacity) b.emit(xyzi, off, out);
+    return b.out_off[(size_t)K];
+}
 int ltrh_io_yaml_get(const char* path, const char* key, char* value, int32_t capacity, double* list, int32_t list_capacity, int32_t* list_n) {
     YamlParams y;
     if (!y.load(path, &g_io_err)) return -1;

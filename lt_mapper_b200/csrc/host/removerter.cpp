@@ -690,25 +690,16 @@ int Removerter::cascade_promote_updated() {
     std::vector<int64_t> off((size_t)K + 1, 0);
     if (owns(C)) CK(ltr_scanset_download(ctx, C.keyframe_scans_updated_, xyzi, total, off.data()));
     // host-side load-time VoxelGrid, keyframes are independent (the reference's loadKeyframes loop is serial; the per-scan
-    // arithmetic and its std::sort are unchanged, only different scans run on different threads)
-    std::vector<HostCloud> grids((size_t)K);
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int k = 0; k < K; ++k) {
-        HostCloud in((size_t)(off[k + 1] - off[k]));
-        for (size_t i = 0; i < in.size(); ++i) {
-            const float* p = &xyzi[(size_t)(off[k] + (int64_t)i) * 4];
-            in[i] = {p[0], p[1], p[2], p[3]};
-        }
-        grids[(size_t)k] = voxel_grid(in, P.downsample_voxel_size, nullptr);
-    }
-    std::vector<int64_t> out_off((size_t)K + 1, 0);
-    for (int k = 0; k < K; ++k) out_off[(size_t)k + 1] = out_off[(size_t)k] + (int64_t)grids[(size_t)k].size();
-    if (!grow(&pin_out_, &pin_out_cap_, (size_t)std::max<int64_t>(out_off[(size_t)K], 1) * 16)) return fail(LTR_ERR_NOMEM, "cascade: pinned staging allocation failed");
-    float* out = (float*)pin_out_;
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int k = 0; k < K; ++k) {
-        float* o = out + (size_t)out_off[(size_t)k] * 4;
-        for (const auto& p : grids[(size_t)k]) { *o++ = p.x; *o++ = p.y; *o++ = p.z; *o++ = p.intensity; }
+    // arithmetic and its std::sort are unchanged, only different scans run on different threads).  Scans that take PCL's overflow
+    // exit -- the common case for 0.05 m leaves on outdoor scans -- go from one staging buffer to the other with a single memcpy.
+    VoxelGridBatch vg;
+    vg.plan(xyzi, off.data(), K, P.downsample_voxel_size);
+    const std::vector<int64_t>& out_off = vg.out_off;
+    const float* out = xyzi;            // every scan passed through unchanged: the downloaded buffer IS the next session's input
+    if (std::find(vg.unchanged.begin(), vg.unchanged.end(), (uint8_t)0) != vg.unchanged.end()) {
+        if (!grow(&pin_out_, &pin_out_cap_, (size_t)std::max<int64_t>(out_off[(size_t)K], 1) * 16)) return fail(LTR_ERR_NOMEM, "cascade: pinned staging allocation failed");
+        vg.emit(xyzi, off.data(), (float*)pin_out_);
+        out = (const float*)pin_out_;
     }
     for (Session* s : {&central_sess_, &query_sess_}) {
         for (auto& kv : s->cloud_names()) if (*kv.second >= 0) { CK(ltr_cloud_free(ctx, *kv.second)); *kv.second = -1; }

@@ -43,7 +43,7 @@ class Comm(ctypes.Structure):
 HOST_EXPORTS = ["ltrh_params_default", "ltrh_create", "ltrh_destroy", "ltrh_last_error", "ltrh_set_comm", "ltrh_context", "ltrh_comm_init_nccl", "ltrh_owns_session", "ltrh_invert_poses",
                 "ltrh_load_session", "ltrh_run_step0", "ltrh_run_step12", "ltrh_run_step3", "ltrh_reset_to_step0", "ltrh_cascade_promote_updated", "ltrh_stage", "ltrh_cloud",
                 "ltrh_scanset", "ltrh_timing", "ltrh_log_count", "ltrh_log_get", "ltrh_io_last_error", "ltrh_io_read_pcd", "ltrh_io_write_pcd",
-                "ltrh_io_read_poses", "ltrh_io_parse_keyframes", "ltrh_io_parse_keyframes_in_roi", "ltrh_io_voxel_grid", "ltrh_io_yaml_get"]
+                "ltrh_io_read_poses", "ltrh_io_parse_keyframes", "ltrh_io_parse_keyframes_in_roi", "ltrh_io_voxel_grid", "ltrh_io_voxel_grid_scans", "ltrh_io_yaml_get"]
 
 
 def host_lib():
@@ -89,6 +89,8 @@ def host_lib():
     L.ltrh_io_parse_keyframes_in_roi.argtypes = [vp, i32, vp, i32, i32, vp, i32]
     L.ltrh_io_voxel_grid.argtypes = [vp, i64, ctypes.c_float, vp, i64, P(i32)]
     L.ltrh_io_voxel_grid.restype = i64
+    L.ltrh_io_voxel_grid_scans.argtypes = [vp, vp, i32, ctypes.c_float, vp, i64, vp]
+    L.ltrh_io_voxel_grid_scans.restype = i64
     L.ltrh_io_yaml_get.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, i32, vp, i32, P(i32)]
     _LIB = L
     return L
@@ -391,6 +393,19 @@ def voxel_grid(xyzi, leaf):
     ov = ctypes.c_int32()
     n = host_lib().ltrh_io_voxel_grid(x.ctypes.data, len(x), leaf, out.ctypes.data, len(out), ctypes.byref(ov))
     return out[:n].copy(), bool(ov.value)
+
+
+def voxel_grid_scans(xyzi, offsets, leaf):
+    """The load-time filter over all scans of a session at once (scan k = rows [offsets[k], offsets[k+1])).  Returns (points, offsets)."""
+    x = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+    off = np.ascontiguousarray(offsets, np.int64)
+    K = len(off) - 1
+    out_off = np.zeros(K + 1, np.int64)
+    out = np.empty((max(len(x), 1), 4), np.float32)     # the filter never grows a scan
+    n = host_lib().ltrh_io_voxel_grid_scans(x.ctypes.data, off.ctypes.data, K, leaf, out.ctypes.data, len(out), out_off.ctypes.data)
+    if n < 0:
+        raise ValueError("ltrh_io_voxel_grid_scans: bad argument")
+    return out[:n].copy(), out_off
 
 
 def yaml_get(path, key):

@@ -89,6 +89,33 @@ def test_voxel_grid_overflow_and_centroids():
     assert np.allclose(out, mean, atol=2e-5)
 
 
+def test_voxel_grid_scans_equals_scan_by_scan():
+    """The batched load-time filter (cascade promotion) == the per-scan filter, bit for bit: pass-through scans (PCL's overflow exit),
+    really voxelised scans, an empty scan and a one-point scan, in one session."""
+    rng = np.random.default_rng(7)
+    scans = [rng.uniform(-90, 90, (4000, 4)).astype(np.float32),            # overflow exit
+             rng.uniform(-3, 3, (30000, 4)).astype(np.float32),             # voxelised (many points per voxel: summation order matters)
+             np.zeros((0, 4), np.float32),
+             rng.uniform(-1, 1, (1, 4)).astype(np.float32),
+             rng.normal(0, 0.4, (15000, 4)).astype(np.float32),             # dense cluster
+             rng.uniform(-80, 80, (2500, 4)).astype(np.float32)]            # overflow exit again (last scan)
+    off = np.concatenate([[0], np.cumsum([len(s) for s in scans])]).astype(np.int64)
+    allp = np.concatenate(scans)
+    for leaf in (0.05, 0.3):
+        got, got_off = removert.voxel_grid_scans(allp, off, leaf)
+        exp = [removert.voxel_grid(s, leaf) for s in scans]
+        assert [int(x) for x in np.diff(got_off)] == [len(e[0]) for e in exp]
+        assert [bool(e[1]) for e in exp] == ([True, False, False, False, False, True] if leaf == 0.05 else [False] * 6)   # mix of both exits
+        for k, (e, _) in enumerate(exp):
+            assert np.array_equal(got[got_off[k]:got_off[k + 1]].view(np.uint32), e.view(np.uint32)), (leaf, k)
+    # all scans pass through: output == input
+    got, got_off = removert.voxel_grid_scans(np.concatenate([scans[0], scans[5]]), np.array([0, 4000, 6500]), 0.05)
+    assert np.array_equal(got_off, [0, 4000, 6500]) and np.array_equal(got, np.concatenate([scans[0], scans[5]]))
+    # no scans at all
+    got, got_off = removert.voxel_grid_scans(np.zeros((0, 4), np.float32), np.array([0]), 0.05)
+    assert len(got) == 0 and list(got_off) == [0]
+
+
 def test_yaml_reader(tmp_path):
     p = str(tmp_path / "params.yaml")
     with open(p, "w") as f:
