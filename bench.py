@@ -420,15 +420,18 @@ def main():
     load()
     R.run_step0()
     n_map = [R.cloud_size("map_global_curr_", s) if R.owns(s) else None for s in (0, 1)]
+    warm_s = 0.0
     for _ in range(args.warmup):
         l2_flush()                    # also warm: the first fill launch loads torch's kernel image (lazy module loading; slow on a cold box)
+        R.ctx.synchronize(); t_w = time.perf_counter()
         R.reset_to_step0(); R.run_step12()
+        R.ctx.synchronize(); warm_s = time.perf_counter() - t_w       # the last warm-up step predicts the length of the timed region
     l2_flush(); R.ctx.synchronize()
     barrier()
     R.ctx.profile_reset()
-    # NVML calls take a driver lock that the launch-heavy step feels (measured: +2.3 % at 50 ms period, none visible at 250 ms): sample slowly
-    # where a step is long, faster where the timed region is short
-    sampler = ClockSampler(local_rank, period_s=0.25 if world <= 2 else 0.1)
+    # NVML calls take a driver lock that the launch-heavy step feels (measured: +2.3 % at 50 ms period, +1.4 % at 250 ms): aim at ~40 samples
+    # over the timed region, never faster than every 50 ms nor slower than every 500 ms
+    sampler = ClockSampler(local_rank, period_s=min(0.5, max(0.05, warm_s * args.steps / 40.0)) if warm_s > 0 else 0.1)
     if not args.no_clock_sampler:
         sampler.start()
     l0 = R.ctx.kernel_launches()
