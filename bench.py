@@ -430,8 +430,8 @@ def main():
     barrier()
     R.ctx.profile_reset()
     # NVML calls take a driver lock that the launch-heavy step feels (measured: +2.3 % at a 50 ms period, none visible at 250 ms): aim at ~40 samples
-    # over the timed region, never faster than every 50 ms nor slower than every 500 ms
-    sampler = ClockSampler(local_rank, period_s=min(0.5, max(0.05, warm_s * args.steps / 40.0)) if warm_s > 0 else 0.1)
+    # over the timed region, never faster than every 100 ms nor slower than every 500 ms
+    sampler = ClockSampler(local_rank, period_s=min(0.5, max(0.1, warm_s * args.steps / 40.0)) if warm_s > 0 else 0.1)
     if not args.no_clock_sampler:
         sampler.start()
     l0 = R.ctx.kernel_launches()
