@@ -31,7 +31,9 @@ import numpy as np
 # torchrun exports OMP_NUM_THREADS=1 to its children; the host-side pieces here that use OpenMP (synthetic scan generation, the load-time
 # VoxelGrid of a cascade promotion, the reference arm) want this rank's share of the cores.  Must happen before libgomp starts.
 if os.environ.get("OMP_NUM_THREADS", "1") == "1":
-    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))))
+    # the reference arm runs on rank 0 alone (the other ranks exit at once): it gets every core
+    _sharers = 1 if any(a in ("reference", "--impl=reference") for a in sys.argv) else max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // _sharers))
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
